@@ -1,0 +1,102 @@
+/*
+ * b200_bridge.h -- C ABI of libb200_bridge.so: the sm_100a kernels behind the drop-in
+ * `BridgeLite` module (reference: src/vlm_bridge/model_architecture/bridge_module.py).
+ *
+ * The reference has no native code and no FFI, so there is no existing
+ * binding to mirror symbol-for-symbol. Each entry point below instead cites the reference call
+ * site(s) whose arithmetic it replaces. INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference adds to call these.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a CUDA device pointer unless stated;
+ *  - the caller owns every buffer (including workspaces); the library never allocates device
+ *    memory and never keeps a pointer after the call returns;
+ *  - every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns without
+ *    synchronising; calls are safe from any host thread;
+ *  - return value: 0 = ok, < 0 = b200b error code, > 0 = cudaError_t. b200b_last_error() returns a
+ *    thread-local human-readable message for the last non-zero return on this thread;
+ *  - bf16 tensors are row-major with 16-byte aligned base pointers and leading dimensions that are
+ *    multiples of 8 elements; fp32 tensors 16-byte aligned, leading dimensions multiples of 4.
+ */
+#ifndef B200_BRIDGE_H_
+#define B200_BRIDGE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200B_ABI_VERSION 1
+
+/* error codes (negative returns) */
+#define B200B_OK 0
+#define B200B_ERR_SHAPE (-1)
+#define B200B_ERR_ALIGN (-2)
+#define B200B_ERR_ARG (-3)
+#define B200B_ERR_DRIVER (-4)
+#define B200B_ERR_TENSORMAP (-5)
+#define B200B_ERR_WORKSPACE (-6)
+#define B200B_ERR_DEVICE (-7)
+
+int b200b_abi_version(void);
+const char* b200b_last_error(void);
+/* number of kernels this library has launched in the calling process (all threads) */
+uint64_t b200b_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------- *
+ * Dropout: Philox4x32-10 keyed by `seed`; each fused op below names the `stream` id it uses so
+ * forward and backward regenerate identical masks. p == 0 disables.
+ * Replaces nn.Dropout / SDPA dropout_p (bridge_module.py:137,235,294,296).
+ * ------------------------------------------------------------------------------------------- */
+
+/* ------------------------------------------------------------------------------------------- *
+ * Dense contraction on tcgen05 tensor cores (TMA-fed, TMEM accumulators), bf16 x bf16 -> fp32.
+ *   acc[m, n] = sum_k A(m, k) * B(n, k)
+ * a_major = 0: A stored [M, K] (K contiguous, lda = row stride);  1: stored [K, M] (M contiguous)
+ * b_major = 0: B stored [N, K] (K contiguous, ldb = row stride);  1: stored [K, N] (N contiguous)
+ * Replaces every nn.Linear forward (bridge_module.py:98-100,118,196-198,216,292,295) and its
+ * autograd dgrad / wgrad.
+ * ------------------------------------------------------------------------------------------- */
+enum b200b_epilogue {
+  /* out bf16 [M,N] = acc + bias                                  (bias may be NULL)            */
+  B200B_EPI_BF16_BIAS = 0,
+  /* aux bf16 = u = acc + bias ; out bf16 = dropout(gelu_erf(u))  (FFN up, bridge_module.py:292-294) */
+  B200B_EPI_BF16_BIAS_GELU = 1,
+  /* out f32 = resid f32 + dropout(bf16(acc + bias))              (residual adds :323,328,333)  */
+  B200B_EPI_F32_BIAS_RESID = 2,
+  /* out bf16 = dropout_bwd(acc) * gelu_erf'(aux)                 (FFN down dgrad)              */
+  B200B_EPI_BF16_DGELU = 3,
+  /* out f32 = beta * out + acc                                   (weight gradients)            */
+  B200B_EPI_F32 = 4
+};
+
+typedef struct b200b_gemm_args {
+  const void* a;
+  const void* b;
+  int32_t a_major, b_major;
+  int32_t m, n, k;
+  int64_t lda, ldb;
+  int32_t epilogue; /* enum b200b_epilogue */
+  int32_t block_n;  /* 0 = choose, else 128 or 256 */
+  void* out;
+  int64_t ldo;
+  void* aux;
+  int64_t ldaux;
+  const float* bias;
+  const float* resid;
+  int64_t ldr;
+  float beta;
+  float dropout_p;
+  uint64_t seed;
+  uint32_t dropout_stream;
+  uint32_t reserved;
+} b200b_gemm_args;
+
+int b200b_gemm(const b200b_gemm_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_BRIDGE_H_ */

@@ -1,0 +1,5 @@
+"""B200-native drop-in for the reference bridge hot path.
+
+Reference: src/vlm_bridge/model_architecture/bridge_module.py (BridgeLite and its blocks).
+"""
+__version__ = "0.1.0"

@@ -1,0 +1,34 @@
+// Host-side helpers shared by the .cu translation units of libb200_bridge.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace b200b {
+
+// records the message returned by b200b_last_error() (thread-local)
+void set_last_error(const char* fmt, ...);
+// cudaGetLastError() after a launch; bumps the process-wide launch counter on success
+int check_launch(const char* what);
+// SM count of the current device (cached per device); fails on non-sm_100 devices
+int device_sm_count(int* out);
+
+inline DropoutCfg make_dropout_cfg(float p, uint64_t seed) {
+  DropoutCfg d;
+  if (p > 0.0f) {
+    uint32_t thr = (uint32_t)(p * 65536.0f + 0.5f);
+    if (thr < 1) thr = 1;
+    if (thr > 65535) thr = 65535;
+    d.thr = thr;
+    d.scale = 1.0f / (1.0f - p);
+  } else {
+    d.thr = 0;
+    d.scale = 1.0f;
+  }
+  d.seed_lo = (uint32_t)seed;
+  d.seed_hi = (uint32_t)(seed >> 32);
+  return d;
+}
+
+}  // namespace b200b
