@@ -96,6 +96,66 @@ typedef struct b200b_gemm_args {
 
 int b200b_gemm(const b200b_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------- *
+ * Row kernels (HBM-bound, vectorised): LayerNorm and the reductions / casts around it.
+ * ------------------------------------------------------------------------------------------- */
+
+/* y bf16[rows,dim] = (x - mean) * rstd * gamma + beta; also writes mean[rows], rstd[rows].
+ * Replaces nn.LayerNorm forward (bridge_module.py:316,326,331) followed by autocast's bf16 cast. */
+int b200b_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16,
+                        float* mean, float* rstd, int rows, int dim, float eps, void* stream);
+
+/* dx f32 = dres + LayerNorm input-gradient(dy bf16, x, mean, rstd, gamma). dres may be NULL and
+ * dx may alias dres. Replaces autograd of nn.LayerNorm plus the residual-branch gradient add. */
+int b200b_layernorm_bwd(const void* dy_bf16, const float* x, const float* mean, const float* rstd,
+                        const float* gamma, const float* dres, float* dx, int rows, int dim,
+                        void* stream);
+
+/* Column sums over rows of dy bf16[rows, cols] (row pitch ld):
+ *   out_sum[c]  = sum_r dy[r,c]                          (nn.Linear bias grads, LayerNorm dbeta)
+ *   out_gsum[c] = sum_r dy[r,c] * (x[r,c]-mean[r])*rstd[r]   (LayerNorm dgamma; x may be NULL)
+ * Deterministic two-stage reduction through `workspace`. */
+size_t b200b_colsum_workspace_bytes(int rows, int cols);
+int b200b_colsum(const void* dy_bf16, int64_t ld, const float* x, const float* mean,
+                 const float* rstd, float* out_sum, float* out_gsum, int rows, int cols,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* out bf16[n] = bf16(in f32[n]); with dropout_p > 0 additionally applies the dropout-backward
+ * mask of `dropout_stream` (element index = position in the range). n % 8 == 0.
+ * Replaces autocast's weight / activation casts and nn.Dropout backward (bridge_module.py:296). */
+int b200b_cast_bf16(const float* in, void* out_bf16, int64_t n, float dropout_p, uint64_t seed,
+                    uint32_t dropout_stream, void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
+ * Fused multi-head attention, softmax(Q K^T / sqrt(d)) V, no mask, non-causal.
+ * Replaces F.scaled_dot_product_attention (bridge_module.py:132-139, 230-237) and the head
+ * split / merge around it (:103-115, :201-213): token t = b*len + i of head h is read at
+ * ptr + t*ld + h*head_dim, so Q/K/V may live inside fused projection outputs.
+ * head_dim in {64, 128, 288}. lse is [batch, heads, len_q] fp32 (log2 domain), written by the
+ * forward and read by the backward. Dropout on the probabilities uses stream `dropout_stream`.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct b200b_attn_args {
+  const void* q; int64_t ldq;
+  const void* k; int64_t ldk;
+  const void* v; int64_t ldv;
+  void* o; int64_t ldo;          /* forward: written; backward: forward output, read */
+  float* lse;
+  const void* d_o; int64_t lddo; /* backward only from here */
+  void* dq; int64_t lddq;
+  void* dk; int64_t lddk;
+  void* dv; int64_t lddv;
+  void* workspace; uint64_t workspace_bytes;
+  int32_t batch, heads, len_q, len_k, head_dim;
+  float dropout_p;
+  uint64_t seed;
+  uint32_t dropout_stream;
+  uint32_t reserved;
+} b200b_attn_args;
+
+int b200b_attention_fwd(const b200b_attn_args* args, void* stream);
+size_t b200b_attention_bwd_workspace_bytes(int batch, int heads, int len_q, int len_k);
+int b200b_attention_bwd(const b200b_attn_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,27 @@ class GemmArgs(C.Structure):
     ]
 
 
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("ldq", C.c_int64),
+        ("k", C.c_void_p), ("ldk", C.c_int64),
+        ("v", C.c_void_p), ("ldv", C.c_int64),
+        ("o", C.c_void_p), ("ldo", C.c_int64),
+        ("lse", C.c_void_p),
+        ("d_o", C.c_void_p), ("lddo", C.c_int64),
+        ("dq", C.c_void_p), ("lddq", C.c_int64),
+        ("dk", C.c_void_p), ("lddk", C.c_int64),
+        ("dv", C.c_void_p), ("lddv", C.c_int64),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
+        ("batch", C.c_int32), ("heads", C.c_int32), ("len_q", C.c_int32), ("len_k", C.c_int32),
+        ("head_dim", C.c_int32),
+        ("dropout_p", C.c_float),
+        ("seed", C.c_uint64),
+        ("dropout_stream", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -62,6 +83,24 @@ def _declare(lib) -> None:
     lib.b200b_launch_count.argtypes = []
     lib.b200b_gemm.restype = C.c_int
     lib.b200b_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+    lib.b200b_layernorm_fwd.restype = C.c_int
+    lib.b200b_layernorm_fwd.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_float, C.c_void_p]
+    lib.b200b_layernorm_bwd.restype = C.c_int
+    lib.b200b_layernorm_bwd.argtypes = [C.c_void_p] * 7 + [C.c_int, C.c_int, C.c_void_p]
+    lib.b200b_colsum_workspace_bytes.restype = C.c_size_t
+    lib.b200b_colsum_workspace_bytes.argtypes = [C.c_int, C.c_int]
+    lib.b200b_colsum.restype = C.c_int
+    lib.b200b_colsum.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p,
+                                                                               C.c_size_t, C.c_void_p]
+    lib.b200b_cast_bf16.restype = C.c_int
+    lib.b200b_cast_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_uint64, C.c_uint32,
+                                    C.c_void_p]
+    lib.b200b_attention_fwd.restype = C.c_int
+    lib.b200b_attention_fwd.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
+    lib.b200b_attention_bwd_workspace_bytes.restype = C.c_size_t
+    lib.b200b_attention_bwd_workspace_bytes.argtypes = [C.c_int] * 4
+    lib.b200b_attention_bwd.restype = C.c_int
+    lib.b200b_attention_bwd.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
 
 
 def lib():

@@ -1,0 +1,668 @@
+// Fused multi-head attention for the bridge (forward + backward), bf16 operands / fp32 softmax.
+//
+// Replaces F.scaled_dot_product_attention at bridge_module.py:132-139 (cross-attention, 8 heads of
+// 288 over 257 / 1370 vision tokens) and :230-237 (non-causal, unmasked self-attention, 18 heads of
+// 128), including the head split/merge views (:103-115, :201-213): Q/K/V are read in place from the
+// projection outputs ([tokens, heads*d] with arbitrary row pitch) and O is written head-merged.
+//
+// Data movement: K/V (and Q/dO) rows are staged into shared memory with TMA bulk copies
+// (cp.async.bulk, one row = one head slice, completion on an mbarrier), double buffered so the
+// copy of key tile t+1 overlaps the math of tile t. Rows are padded by 16 bytes in shared memory,
+// which makes every ldmatrix access bank-conflict free for d in {64, 128, 288}.
+// Math: mma.sync m16n8k16 (bf16 -> fp32); online softmax in the exp2 domain with the row max / row
+// sum reduced across the 4 lanes that share a row via warp shuffles; O and dQ accumulators
+// (16 rows x d per warp) live in registers.
+//
+// Backward is three kernels: row dots delta = sum(dO*O); a query-major pass that recomputes
+// P from the saved log-sum-exp, forms dS, accumulates dQ and spills P(dropped) and dS as bf16 to a
+// scratch [B,H,Lq,Lkp]; and a key-major pass dV = P^T dO, dK = dS^T Q that reads that scratch.
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "launch.h"
+
+namespace b200b {
+
+struct AttnParams {
+  const __nv_bfloat16* q; long long ldq;
+  const __nv_bfloat16* k; long long ldk;
+  const __nv_bfloat16* v; long long ldv;
+  __nv_bfloat16* o; long long ldo;        // fwd: output; bwd: forward output (read)
+  const __nv_bfloat16* d_o; long long lddo;
+  __nv_bfloat16* dq; long long lddq;
+  __nv_bfloat16* dk; long long lddk;
+  __nv_bfloat16* dv; long long lddv;
+  float* lse2;                             // [B,H,Lq] log2-domain log-sum-exp of the scaled scores
+  float* delta;                            // [B,H,Lq]
+  __nv_bfloat16* p_scr;                    // [B,H,Lq,Lkp] dropped probabilities
+  __nv_bfloat16* ds_scr;                   // [B,H,Lq,Lkp] dS (unscaled)
+  int B, H, Lq, Lk, Lkp;
+  float scale, scale_log2;
+  DropoutCfg drop;
+  uint32_t drop_stream;
+};
+
+template <int HD>
+struct AttnCfg {
+  static constexpr int kBM = 64;                      // query rows per CTA: 4 warps x 16
+  static constexpr int kBN = (HD > 128) ? 32 : 64;    // keys per tile
+  static constexpr int kLd = HD + 8;                  // padded smem row, elements
+  static constexpr int kRowBytes = HD * 2;
+  static constexpr int kQT = 32;                      // query rows per step of the key-major pass
+  static constexpr int kScrLd = 40;                   // padded scratch-tile row (32 keys + 8)
+  static constexpr size_t kFwdSmem = (size_t)(kBM + 4 * kBN) * kLd * 2;
+  static constexpr size_t kBwdQSmem = (size_t)(2 * kBM + 4 * kBN) * kLd * 2;
+  static constexpr size_t kBwdKVSmem = (size_t)2 * (2 * kQT * kScrLd + 2 * kQT * kLd) * 2;
+};
+
+__device__ __forceinline__ void zero_row(__nv_bfloat16* row, int bytes, int lane, int nlanes) {
+  for (int c = lane * 16; c < bytes; c += nlanes * 16)
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(row) + c) = make_uint4(0, 0, 0, 0);
+}
+
+// Stage one K/V tile (keys [j0, j0+kBN) of sample b, head h) into `ks`/`vs`; executed by warp 0.
+template <int HD>
+__device__ __forceinline__ void issue_kv_tile(const AttnParams& p, int b, int h, int j0, __nv_bfloat16* ks,
+                                              __nv_bfloat16* vs, uint64_t* bar, int lane) {
+  using Cfg = AttnCfg<HD>;
+  const int nk = min(Cfg::kBN, p.Lk - j0);
+  // rows past the end of the sequence must read as zeros (0 * garbage could be NaN)
+  for (int r = nk; r < Cfg::kBN; ++r) {
+    zero_row(ks + (size_t)r * Cfg::kLd, Cfg::kRowBytes, lane, 32);
+    zero_row(vs + (size_t)r * Cfg::kLd, Cfg::kRowBytes, lane, 32);
+  }
+  if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(2 * nk * Cfg::kRowBytes));
+  __syncwarp();
+  for (int r = lane; r < nk; r += 32) {
+    const size_t grow = (size_t)b * p.Lk + j0 + r;
+    bulk_load_1d(ks + (size_t)r * Cfg::kLd, p.k + grow * p.ldk + (size_t)h * HD, Cfg::kRowBytes, bar);
+    bulk_load_1d(vs + (size_t)r * Cfg::kLd, p.v + grow * p.ldv + (size_t)h * HD, Cfg::kRowBytes, bar);
+  }
+}
+
+// S[16 x BN] (+)= A[16 x HD] * Bt[BN x HD]^T with A rows at `a_rows` and Bt rows at `b_rows` (both
+// padded row-major in shared memory). Used for Q K^T and dO V^T.
+template <int HD, int BN>
+__device__ __forceinline__ void mma_rows_x_rows(float (&s)[BN / 8][4], const __nv_bfloat16* a_rows,
+                                                const __nv_bfloat16* b_rows, int lane) {
+  constexpr int kLd = HD + 8;
+  const uint32_t a_base = smem_u32(a_rows + (size_t)(lane & 15) * kLd + (lane >> 4) * 8);
+  const uint32_t b_base = smem_u32(b_rows + (size_t)((lane & 7) + ((lane >> 4) << 3)) * kLd + ((lane >> 3) & 1) * 8);
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ++ks) {
+    uint32_t a[4];
+    ldmatrix_x4(a, a_base + ks * 32);
+#pragma unroll
+    for (int np = 0; np < BN / 16; ++np) {
+      uint32_t bb[4];
+      ldmatrix_x4(bb, b_base + (uint32_t)(np * 16 * kLd * 2) + ks * 32);
+      const uint32_t b0[2] = {bb[0], bb[1]}, b1[2] = {bb[2], bb[3]};
+      mma_m16n8k16(s[2 * np], a, b0);
+      mma_m16n8k16(s[2 * np + 1], a, b1);
+    }
+  }
+}
+
+// acc[16 x HD] += P[16 x BN] (bf16 A fragments built from the C-fragment layout) * Bk[BN x HD]
+// with Bk rows (the contraction index) in padded row-major shared memory. Used for P V and dS K.
+template <int HD, int BN>
+__device__ __forceinline__ void mma_frag_x_cols(float (&acc)[HD / 8][4], const float (&pf)[BN / 8][4],
+                                                const __nv_bfloat16* b_rows, int lane) {
+  constexpr int kLd = HD + 8;
+  const uint32_t b_base = smem_u32(b_rows + (size_t)((lane & 7) + ((lane >> 3) & 1) * 8) * kLd + (lane >> 4) * 8);
+#pragma unroll
+  for (int kk = 0; kk < BN / 16; ++kk) {
+    uint32_t a[4];
+    a[0] = pack_bf16(pf[2 * kk][0], pf[2 * kk][1]);
+    a[1] = pack_bf16(pf[2 * kk][2], pf[2 * kk][3]);
+    a[2] = pack_bf16(pf[2 * kk + 1][0], pf[2 * kk + 1][1]);
+    a[3] = pack_bf16(pf[2 * kk + 1][2], pf[2 * kk + 1][3]);
+#pragma unroll
+    for (int dp = 0; dp < HD / 16; ++dp) {
+      uint32_t bb[4];
+      ldmatrix_x4_trans(bb, b_base + (uint32_t)(kk * 16 * kLd * 2) + dp * 32);
+      const uint32_t b0[2] = {bb[0], bb[1]}, b1[2] = {bb[2], bb[3]};
+      mma_m16n8k16(acc[2 * dp], a, b0);
+      mma_m16n8k16(acc[2 * dp + 1], a, b1);
+    }
+  }
+}
+
+// Write this warp's 16 x HD accumulator (scaled) as bf16 through its own staging rows, then copy
+// the rows out with 16-byte coalesced stores.
+template <int HD>
+__device__ __forceinline__ void store_rows_bf16(const float (&acc)[HD / 8][4], float s0, float s1,
+                                                __nv_bfloat16* stage_rows /*16 rows, padded*/,
+                                                __nv_bfloat16* gdst /*row 0 of this warp*/, long long ld,
+                                                int rows_valid, int lane) {
+  constexpr int kLd = HD + 8;
+  const int g = lane >> 2, t = lane & 3;
+  __syncwarp();
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) {
+    *reinterpret_cast<uint32_t*>(stage_rows + (size_t)g * kLd + n * 8 + 2 * t) = pack_bf16(acc[n][0] * s0, acc[n][1] * s0);
+    *reinterpret_cast<uint32_t*>(stage_rows + (size_t)(g + 8) * kLd + n * 8 + 2 * t) =
+        pack_bf16(acc[n][2] * s1, acc[n][3] * s1);
+  }
+  __syncwarp();
+  constexpr int kChunks = HD / 8;  // 16-byte chunks per row
+  for (int idx = lane; idx < 16 * kChunks; idx += 32) {
+    const int r = idx / kChunks, c = idx % kChunks;
+    if (r < rows_valid)
+      *reinterpret_cast<uint4*>(gdst + (size_t)r * ld + c * 8) =
+          *reinterpret_cast<const uint4*>(stage_rows + (size_t)r * kLd + c * 8);
+  }
+}
+
+// ================================================================================================
+// forward
+// ================================================================================================
+template <int HD>
+__global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
+  using Cfg = AttnCfg<HD>;
+  constexpr int BN = Cfg::kBN, kLd = Cfg::kLd;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+  __nv_bfloat16* Ks = Qs + (size_t)Cfg::kBM * kLd;   // [2][BN][kLd]
+  __nv_bfloat16* Vs = Ks + (size_t)2 * BN * kLd;     // [2][BN][kLd]
+  __shared__ __align__(8) uint64_t qbar, full_bar[2];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * Cfg::kBM;
+  const int nq = min(Cfg::kBM, p.Lq - q0);
+  const int nt = (p.Lk + BN - 1) / BN;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&qbar, 1);
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0) mbar_arrive_expect_tx(&qbar, (uint32_t)(nq * Cfg::kRowBytes));
+    __syncwarp();
+    for (int r = lane; r < nq; r += 32)
+      bulk_load_1d(Qs + (size_t)r * kLd, p.q + ((size_t)b * p.Lq + q0 + r) * p.ldq + (size_t)h * HD, Cfg::kRowBytes,
+                   &qbar);
+    issue_kv_tile<HD>(p, b, h, 0, Ks, Vs, &full_bar[0], lane);
+  }
+  __syncthreads();  // zero-filled rows visible to all warps
+
+  float o_acc[HD / 8][4];
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) o_acc[n][0] = o_acc[n][1] = o_acc[n][2] = o_acc[n][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const int g = lane >> 2, t4 = lane & 3;
+  const size_t bh = (size_t)b * p.H + h;
+
+  mbar_wait(&qbar, 0);
+  for (int t = 0; t < nt; ++t) {
+    const int stage = t & 1;
+    if (warp == 0 && t + 1 < nt)
+      issue_kv_tile<HD>(p, b, h, (t + 1) * BN, Ks + (size_t)(stage ^ 1) * BN * kLd, Vs + (size_t)(stage ^ 1) * BN * kLd,
+                        &full_bar[stage ^ 1], lane);
+    mbar_wait(&full_bar[stage], (uint32_t)((t >> 1) & 1));
+
+    float s[BN / 8][4];
+#pragma unroll
+    for (int n = 0; n < BN / 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+    mma_rows_x_rows<HD, BN>(s, Qs + (size_t)warp * 16 * kLd, Ks + (size_t)stage * BN * kLd, lane);
+
+    const int j0 = t * BN;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < BN / 8; ++n) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = j0 + n * 8 + 2 * t4 + (e & 1);
+        s[n][e] = (col < p.Lk) ? s[n][e] * p.scale_log2 : -INFINITY;
+      }
+      mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
+    }
+    // the 4 lanes of a quad share rows g and g+8
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m_run[0], mx0), mn1 = fmaxf(m_run[1], mx1);
+    const float al0 = exp2f(m_run[0] - mn0), al1 = exp2f(m_run[1] - mn1);
+    m_run[0] = mn0;
+    m_run[1] = mn1;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < BN / 8; ++n) {
+      s[n][0] = exp2f(s[n][0] - mn0);
+      s[n][1] = exp2f(s[n][1] - mn0);
+      s[n][2] = exp2f(s[n][2] - mn1);
+      s[n][3] = exp2f(s[n][3] - mn1);
+      rs0 += s[n][0] + s[n][1];
+      rs1 += s[n][2] + s[n][3];
+    }
+    l_run[0] = l_run[0] * al0 + rs0;
+    l_run[1] = l_run[1] * al1 + rs1;
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n) {
+      o_acc[n][0] *= al0; o_acc[n][1] *= al0;
+      o_acc[n][2] *= al1; o_acc[n][3] *= al1;
+    }
+    if (p.drop.thr != 0) {
+      const uint64_t r0 = (bh * p.Lq + (uint64_t)(q0 + warp * 16 + g)) * (uint64_t)p.Lkp;
+      const uint64_t r1 = r0 + (uint64_t)8 * p.Lkp;
+#pragma unroll
+      for (int n = 0; n < BN / 8; ++n) {
+        const uint4 b0 = dropout_bits8(p.drop, p.drop_stream, (r0 + j0 + n * 8) >> 3);
+        const uint4 b1 = dropout_bits8(p.drop, p.drop_stream, (r1 + j0 + n * 8) >> 3);
+        s[n][0] = dropout_keep(b0, 2 * t4, p.drop.thr) ? s[n][0] * p.drop.scale : 0.f;
+        s[n][1] = dropout_keep(b0, 2 * t4 + 1, p.drop.thr) ? s[n][1] * p.drop.scale : 0.f;
+        s[n][2] = dropout_keep(b1, 2 * t4, p.drop.thr) ? s[n][2] * p.drop.scale : 0.f;
+        s[n][3] = dropout_keep(b1, 2 * t4 + 1, p.drop.thr) ? s[n][3] * p.drop.scale : 0.f;
+      }
+    }
+    mma_frag_x_cols<HD, BN>(o_acc, s, Vs + (size_t)stage * BN * kLd, lane);
+    __syncthreads();  // everyone is done with this stage before it is refilled
+  }
+
+  l_run[0] += __shfl_xor_sync(0xffffffffu, l_run[0], 1);
+  l_run[0] += __shfl_xor_sync(0xffffffffu, l_run[0], 2);
+  l_run[1] += __shfl_xor_sync(0xffffffffu, l_run[1], 1);
+  l_run[1] += __shfl_xor_sync(0xffffffffu, l_run[1], 2);
+  const int row0 = q0 + warp * 16 + g;
+  if (t4 == 0) {
+    if (row0 < p.Lq) p.lse2[bh * p.Lq + row0] = m_run[0] + log2f(l_run[0]);
+    if (row0 + 8 < p.Lq) p.lse2[bh * p.Lq + row0 + 8] = m_run[1] + log2f(l_run[1]);
+  }
+  const int rows_valid = max(0, min(16, nq - warp * 16));
+  store_rows_bf16<HD>(o_acc, 1.0f / l_run[0], 1.0f / l_run[1], Qs + (size_t)warp * 16 * kLd,
+                      p.o + ((size_t)b * p.Lq + q0 + warp * 16) * p.ldo + (size_t)h * HD, p.ldo, rows_valid, lane);
+}
+
+// ================================================================================================
+// backward: delta[b,h,i] = sum_c dO[i, h, c] * O[i, h, c]; one warp per (token, head)
+// ================================================================================================
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo,
+                                  const __nv_bfloat16* __restrict__ d_o, long long lddo, float* __restrict__ delta,
+                                  int B, int H, int Lq, int HD) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = blockIdx.x;  // b * Lq + i
+  if (warp >= H) return;
+  const uint32_t* po = reinterpret_cast<const uint32_t*>(o + row * ldo + (size_t)warp * HD);
+  const uint32_t* pd = reinterpret_cast<const uint32_t*>(d_o + row * lddo + (size_t)warp * HD);
+  float s = 0.f;
+  for (int c = lane; c < HD / 2; c += 32) {
+    const uint32_t a = po[c], d = pd[c];
+    s += bf16_lo(a) * bf16_lo(d) + bf16_hi(a) * bf16_hi(d);
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    const long long b = row / Lq, i = row % Lq;
+    delta[((size_t)b * H + warp) * Lq + i] = s;
+  }
+}
+
+// ================================================================================================
+// backward, query-major: dQ, plus bf16 spills of dropped P and of dS for the key-major pass
+// ================================================================================================
+template <int HD>
+__global__ void __launch_bounds__(128) attn_bwd_q_kernel(const AttnParams p) {
+  using Cfg = AttnCfg<HD>;
+  constexpr int BN = Cfg::kBN, kLd = Cfg::kLd;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+  __nv_bfloat16* dOs = Qs + (size_t)Cfg::kBM * kLd;
+  __nv_bfloat16* Ks = dOs + (size_t)Cfg::kBM * kLd;
+  __nv_bfloat16* Vs = Ks + (size_t)2 * BN * kLd;
+  __shared__ __align__(8) uint64_t qbar, full_bar[2];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * Cfg::kBM;
+  const int nq = min(Cfg::kBM, p.Lq - q0);
+  const int nt = (p.Lk + BN - 1) / BN;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&qbar, 1);
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0) mbar_arrive_expect_tx(&qbar, (uint32_t)(2 * nq * Cfg::kRowBytes));
+    __syncwarp();
+    for (int r = lane; r < nq; r += 32) {
+      const size_t grow = (size_t)b * p.Lq + q0 + r;
+      bulk_load_1d(Qs + (size_t)r * kLd, p.q + grow * p.ldq + (size_t)h * HD, Cfg::kRowBytes, &qbar);
+      bulk_load_1d(dOs + (size_t)r * kLd, p.d_o + grow * p.lddo + (size_t)h * HD, Cfg::kRowBytes, &qbar);
+    }
+    issue_kv_tile<HD>(p, b, h, 0, Ks, Vs, &full_bar[0], lane);
+  }
+  __syncthreads();
+
+  float dq_acc[HD / 8][4];
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) dq_acc[n][0] = dq_acc[n][1] = dq_acc[n][2] = dq_acc[n][3] = 0.f;
+  const int g = lane >> 2, t4 = lane & 3;
+  const size_t bh = (size_t)b * p.H + h;
+  const int row0 = q0 + warp * 16 + g, row1 = row0 + 8;
+  const bool ok0 = row0 < p.Lq, ok1 = row1 < p.Lq;
+  const float lse0 = ok0 ? p.lse2[bh * p.Lq + row0] : 0.f, lse1 = ok1 ? p.lse2[bh * p.Lq + row1] : 0.f;
+  const float del0 = ok0 ? p.delta[bh * p.Lq + row0] : 0.f, del1 = ok1 ? p.delta[bh * p.Lq + row1] : 0.f;
+  const uint64_t ridx0 = (bh * p.Lq + (uint64_t)row0) * (uint64_t)p.Lkp;
+  const uint64_t ridx1 = ridx0 + (uint64_t)8 * p.Lkp;
+
+  mbar_wait(&qbar, 0);
+  for (int t = 0; t < nt; ++t) {
+    const int stage = t & 1;
+    if (warp == 0 && t + 1 < nt)
+      issue_kv_tile<HD>(p, b, h, (t + 1) * BN, Ks + (size_t)(stage ^ 1) * BN * kLd, Vs + (size_t)(stage ^ 1) * BN * kLd,
+                        &full_bar[stage ^ 1], lane);
+    mbar_wait(&full_bar[stage], (uint32_t)((t >> 1) & 1));
+
+    float s[BN / 8][4], dp[BN / 8][4];
+#pragma unroll
+    for (int n = 0; n < BN / 8; ++n) {
+      s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+      dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+    }
+    mma_rows_x_rows<HD, BN>(s, Qs + (size_t)warp * 16 * kLd, Ks + (size_t)stage * BN * kLd, lane);
+    mma_rows_x_rows<HD, BN>(dp, dOs + (size_t)warp * 16 * kLd, Vs + (size_t)stage * BN * kLd, lane);
+
+    const int j0 = t * BN;
+#pragma unroll
+    for (int n = 0; n < BN / 8; ++n) {
+      uint4 b0 = make_uint4(0, 0, 0, 0), b1 = make_uint4(0, 0, 0, 0);
+      if (p.drop.thr != 0) {
+        b0 = dropout_bits8(p.drop, p.drop_stream, (ridx0 + j0 + n * 8) >> 3);
+        b1 = dropout_bits8(p.drop, p.drop_stream, (ridx1 + j0 + n * 8) >> 3);
+      }
+      float pd[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = j0 + n * 8 + 2 * t4 + (e & 1);
+        const float lse = (e < 2) ? lse0 : lse1, del = (e < 2) ? del0 : del1;
+        float pr = (col < p.Lk) ? exp2f(s[n][e] * p.scale_log2 - lse) : 0.f;
+        float dpr = dp[n][e];
+        float prd = pr;
+        if (p.drop.thr != 0) {
+          const bool keep = dropout_keep((e < 2) ? b0 : b1, 2 * t4 + (e & 1), p.drop.thr);
+          prd = keep ? pr * p.drop.scale : 0.f;
+          dpr = keep ? dpr * p.drop.scale : 0.f;
+        }
+        pd[e] = prd;
+        s[n][e] = pr * (dpr - del);  // dS (without the softmax scale)
+      }
+      const int colp = j0 + n * 8 + 2 * t4;
+      if (colp < p.Lkp) {
+        if (ok0) {
+          *reinterpret_cast<uint32_t*>(p.p_scr + ridx0 + colp) = pack_bf16(pd[0], pd[1]);
+          *reinterpret_cast<uint32_t*>(p.ds_scr + ridx0 + colp) = pack_bf16(s[n][0], s[n][1]);
+        }
+        if (ok1) {
+          *reinterpret_cast<uint32_t*>(p.p_scr + ridx1 + colp) = pack_bf16(pd[2], pd[3]);
+          *reinterpret_cast<uint32_t*>(p.ds_scr + ridx1 + colp) = pack_bf16(s[n][2], s[n][3]);
+        }
+      }
+    }
+    mma_frag_x_cols<HD, BN>(dq_acc, s, Ks + (size_t)stage * BN * kLd, lane);
+    __syncthreads();
+  }
+  const int rows_valid = max(0, min(16, nq - warp * 16));
+  store_rows_bf16<HD>(dq_acc, p.scale, p.scale, Qs + (size_t)warp * 16 * kLd,
+                      p.dq + ((size_t)b * p.Lq + q0 + warp * 16) * p.lddq + (size_t)h * HD, p.lddq, rows_valid, lane);
+}
+
+// ================================================================================================
+// backward, key-major: dV = Pd^T dO, dK = scale * dS^T Q. CTA = 32 keys; warps 0,1 -> dV of the
+// two 16-key groups, warps 2,3 -> dK. The contraction runs over query rows in steps of 32.
+// ================================================================================================
+template <int HD>
+__global__ void __launch_bounds__(128) attn_bwd_kv_kernel(const AttnParams p) {
+  using Cfg = AttnCfg<HD>;
+  constexpr int QT = Cfg::kQT, kLd = Cfg::kLd, SL = Cfg::kScrLd;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  // per stage: Ps[QT][SL], dSs[QT][SL], dOs[QT][kLd], Qs[QT][kLd]
+  constexpr size_t kStageElems = (size_t)2 * QT * SL + (size_t)2 * QT * kLd;
+  __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+  __shared__ __align__(8) uint64_t full_bar[2];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * 32;
+  const int nkeys = min(32, p.Lkp - j0);  // multiple of 8
+  const int nt = (p.Lq + QT - 1) / QT;
+  const size_t bh = (size_t)b * p.H + h;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int t) {  // warp 0
+    const int stage = t & 1;
+    __nv_bfloat16* Ps = base + (size_t)stage * kStageElems;
+    __nv_bfloat16* dSs = Ps + (size_t)QT * SL;
+    __nv_bfloat16* dOs = dSs + (size_t)QT * SL;
+    __nv_bfloat16* Qs = dOs + (size_t)QT * kLd;
+    const int i0 = t * QT;
+    const int nr = min(QT, p.Lq - i0);
+    for (int r = nr; r < QT; ++r) {  // rows past the sequence end are contraction terms: must be 0
+      zero_row(Ps + (size_t)r * SL, 64, lane, 32);
+      zero_row(dSs + (size_t)r * SL, 64, lane, 32);
+      zero_row(dOs + (size_t)r * kLd, Cfg::kRowBytes, lane, 32);
+      zero_row(Qs + (size_t)r * kLd, Cfg::kRowBytes, lane, 32);
+    }
+    if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(nr * (2 * nkeys * 2 + 2 * Cfg::kRowBytes)));
+    __syncwarp();
+    if (lane < nr) {
+      const int r = lane;
+      const size_t srow = (bh * p.Lq + (size_t)(i0 + r)) * (size_t)p.Lkp + j0;
+      const size_t grow = (size_t)b * p.Lq + i0 + r;
+      bulk_load_1d(Ps + (size_t)r * SL, p.p_scr + srow, (uint32_t)(nkeys * 2), &full_bar[stage]);
+      bulk_load_1d(dSs + (size_t)r * SL, p.ds_scr + srow, (uint32_t)(nkeys * 2), &full_bar[stage]);
+      bulk_load_1d(dOs + (size_t)r * kLd, p.d_o + grow * p.lddo + (size_t)h * HD, Cfg::kRowBytes, &full_bar[stage]);
+      bulk_load_1d(Qs + (size_t)r * kLd, p.q + grow * p.ldq + (size_t)h * HD, Cfg::kRowBytes, &full_bar[stage]);
+    }
+  };
+
+  if (warp == 0) issue(0);
+  __syncthreads();
+
+  float acc[HD / 8][4];
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+  const int kg = warp & 1, which = warp >> 1;  // which: 0 = dV, 1 = dK
+
+  for (int t = 0; t < nt; ++t) {
+    const int stage = t & 1;
+    if (warp == 0 && t + 1 < nt) issue(t + 1);
+    mbar_wait(&full_bar[stage], (uint32_t)((t >> 1) & 1));
+    const __nv_bfloat16* Ps = base + (size_t)stage * kStageElems;
+    const __nv_bfloat16* dSs = Ps + (size_t)QT * SL;
+    const __nv_bfloat16* dOs = dSs + (size_t)QT * SL;
+    const __nv_bfloat16* Qs = dOs + (size_t)QT * kLd;
+    const __nv_bfloat16* A = which ? dSs : Ps;    // [q rows][keys]  -> A^T via ldmatrix.trans
+    const __nv_bfloat16* Bm = which ? Qs : dOs;   // [q rows][HD]
+    const uint32_t a_base = smem_u32(A + (size_t)((lane & 7) + (lane >> 4) * 8) * SL + kg * 16 + ((lane >> 3) & 1) * 8);
+    const uint32_t b_base = smem_u32(Bm + (size_t)((lane & 7) + ((lane >> 3) & 1) * 8) * kLd + (lane >> 4) * 8);
+#pragma unroll
+    for (int kk = 0; kk < QT / 16; ++kk) {
+      uint32_t a[4];
+      ldmatrix_x4_trans(a, a_base + (uint32_t)(kk * 16 * SL * 2));
+#pragma unroll
+      for (int dpi = 0; dpi < HD / 16; ++dpi) {
+        uint32_t bb[4];
+        ldmatrix_x4_trans(bb, b_base + (uint32_t)(kk * 16 * kLd * 2) + dpi * 32);
+        const uint32_t b0[2] = {bb[0], bb[1]}, b1[2] = {bb[2], bb[3]};
+        mma_m16n8k16(acc[2 * dpi], a, b0);
+        mma_m16n8k16(acc[2 * dpi + 1], a, b1);
+      }
+    }
+    __syncthreads();
+  }
+
+  const int g = lane >> 2, t4 = lane & 3;
+  const float sc = which ? p.scale : 1.0f;
+  __nv_bfloat16* dst = which ? p.dk : p.dv;
+  const long long ldd = which ? p.lddk : p.lddv;
+  const int key0 = j0 + kg * 16 + g, key1 = key0 + 8;
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) {
+    const int c = n * 8 + 2 * t4;
+    if (key0 < p.Lk)
+      *reinterpret_cast<uint32_t*>(dst + ((size_t)b * p.Lk + key0) * ldd + (size_t)h * HD + c) =
+          pack_bf16(acc[n][0] * sc, acc[n][1] * sc);
+    if (key1 < p.Lk)
+      *reinterpret_cast<uint32_t*>(dst + ((size_t)b * p.Lk + key1) * ldd + (size_t)h * HD + c) =
+          pack_bf16(acc[n][2] * sc, acc[n][3] * sc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+template <typename K>
+static int set_smem(K kern, size_t bytes, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    set_last_error("%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return B200B_OK;
+}
+
+template <int HD>
+static int launch_fwd(const AttnParams& p, cudaStream_t stream) {
+  using Cfg = AttnCfg<HD>;
+  int rc = set_smem(attn_fwd_kernel<HD>, Cfg::kFwdSmem, "attn_fwd");
+  if (rc) return rc;
+  dim3 grid((p.Lq + Cfg::kBM - 1) / Cfg::kBM, p.H, p.B);
+  attn_fwd_kernel<HD><<<grid, 128, Cfg::kFwdSmem, stream>>>(p);
+  return check_launch("attn_fwd");
+}
+
+template <int HD>
+static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
+  using Cfg = AttnCfg<HD>;
+  int rc = set_smem(attn_bwd_q_kernel<HD>, Cfg::kBwdQSmem, "attn_bwd_q");
+  if (rc) return rc;
+  rc = set_smem(attn_bwd_kv_kernel<HD>, Cfg::kBwdKVSmem, "attn_bwd_kv");
+  if (rc) return rc;
+  const int delta_threads = 32 * p.H;
+  attn_delta_kernel<<<p.B * p.Lq, delta_threads, 0, stream>>>(p.o, p.ldo, p.d_o, p.lddo, p.delta, p.B, p.H, p.Lq, HD);
+  rc = check_launch("attn_delta");
+  if (rc) return rc;
+  dim3 gq((p.Lq + Cfg::kBM - 1) / Cfg::kBM, p.H, p.B);
+  attn_bwd_q_kernel<HD><<<gq, 128, Cfg::kBwdQSmem, stream>>>(p);
+  rc = check_launch("attn_bwd_q");
+  if (rc) return rc;
+  dim3 gk((p.Lk + 31) / 32, p.H, p.B);
+  attn_bwd_kv_kernel<HD><<<gk, 128, Cfg::kBwdKVSmem, stream>>>(p);
+  return check_launch("attn_bwd_kv");
+}
+
+static bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int validate_common(const b200b_attn_args* a, const char* what) {
+  if (a == nullptr || !a->q || !a->k || !a->v || !a->o || !a->lse) {
+    set_last_error("%s: null argument", what);
+    return B200B_ERR_ARG;
+  }
+  if (a->batch <= 0 || a->heads <= 0 || a->heads > 32 || a->len_q <= 0 || a->len_k <= 0) {
+    set_last_error("%s: bad sizes (batch=%d heads=%d len_q=%d len_k=%d)", what, a->batch, a->heads, a->len_q, a->len_k);
+    return B200B_ERR_SHAPE;
+  }
+  if (a->head_dim != 64 && a->head_dim != 128 && a->head_dim != 288) {
+    set_last_error("%s: head_dim %d not built (64, 128, 288)", what, a->head_dim);
+    return B200B_ERR_SHAPE;
+  }
+  if (!al16p(a->q) || !al16p(a->k) || !al16p(a->v) || !al16p(a->o) || (a->ldq % 8) || (a->ldk % 8) || (a->ldv % 8) ||
+      (a->ldo % 8)) {
+    set_last_error("%s: q/k/v/o must be 16-byte aligned with row pitch multiple of 8 elements", what);
+    return B200B_ERR_ALIGN;
+  }
+  if (!(a->dropout_p >= 0.0f && a->dropout_p < 1.0f)) {
+    set_last_error("%s: dropout_p must be in [0,1)", what);
+    return B200B_ERR_ARG;
+  }
+  return B200B_OK;
+}
+
+static AttnParams make_params(const b200b_attn_args* a) {
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = reinterpret_cast<const __nv_bfloat16*>(a->q); p.ldq = a->ldq;
+  p.k = reinterpret_cast<const __nv_bfloat16*>(a->k); p.ldk = a->ldk;
+  p.v = reinterpret_cast<const __nv_bfloat16*>(a->v); p.ldv = a->ldv;
+  p.o = reinterpret_cast<__nv_bfloat16*>(a->o); p.ldo = a->ldo;
+  p.lse2 = a->lse;
+  p.B = a->batch; p.H = a->heads; p.Lq = a->len_q; p.Lk = a->len_k;
+  p.Lkp = (a->len_k + 7) & ~7;
+  p.scale = 1.0f / sqrtf((float)a->head_dim);
+  p.scale_log2 = p.scale * 1.4426950408889634f;
+  p.drop = make_dropout_cfg(a->dropout_p, a->seed);
+  p.drop_stream = a->dropout_stream;
+  return p;
+}
+
+}  // namespace b200b
+
+using namespace b200b;
+
+extern "C" int b200b_attention_fwd(const b200b_attn_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int rc = validate_common(a, "attention_fwd");
+  if (rc) return rc;
+  AttnParams p = make_params(a);
+  switch (a->head_dim) {
+    case 64: return launch_fwd<64>(p, stream);
+    case 128: return launch_fwd<128>(p, stream);
+    default: return launch_fwd<288>(p, stream);
+  }
+}
+
+extern "C" size_t b200b_attention_bwd_workspace_bytes(int batch, int heads, int len_q, int len_k) {
+  const size_t lkp = ((size_t)len_k + 7) & ~(size_t)7;
+  const size_t rows = (size_t)batch * heads * len_q;
+  // delta (fp32, padded to 16 B) + two bf16 scratch matrices
+  return ((rows * 4 + 255) & ~(size_t)255) + 2 * ((rows * lkp * 2 + 255) & ~(size_t)255);
+}
+
+extern "C" int b200b_attention_bwd(const b200b_attn_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int rc = validate_common(a, "attention_bwd");
+  if (rc) return rc;
+  if (!a->d_o || !a->dq || !a->dk || !a->dv || !a->workspace) {
+    set_last_error("attention_bwd: null gradient / workspace pointer");
+    return B200B_ERR_ARG;
+  }
+  if (!al16p(a->d_o) || !al16p(a->dq) || !al16p(a->dk) || !al16p(a->dv) || !al16p(a->workspace) || (a->lddo % 8) ||
+      (a->lddq % 8) || (a->lddk % 8) || (a->lddv % 8)) {
+    set_last_error("attention_bwd: gradients must be 16-byte aligned with row pitch multiple of 8 elements");
+    return B200B_ERR_ALIGN;
+  }
+  const size_t need = b200b_attention_bwd_workspace_bytes(a->batch, a->heads, a->len_q, a->len_k);
+  if (a->workspace_bytes < need) {
+    set_last_error("attention_bwd: workspace too small (%zu < %zu)", (size_t)a->workspace_bytes, need);
+    return B200B_ERR_WORKSPACE;
+  }
+  AttnParams p = make_params(a);
+  p.d_o = reinterpret_cast<const __nv_bfloat16*>(a->d_o); p.lddo = a->lddo;
+  p.dq = reinterpret_cast<__nv_bfloat16*>(a->dq); p.lddq = a->lddq;
+  p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.lddk = a->lddk;
+  p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv); p.lddv = a->lddv;
+  const size_t rows = (size_t)a->batch * a->heads * a->len_q;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
+  p.delta = reinterpret_cast<float*>(ws);
+  const size_t off1 = (rows * 4 + 255) & ~(size_t)255;
+  const size_t scr = (rows * (size_t)p.Lkp * 2 + 255) & ~(size_t)255;
+  p.p_scr = reinterpret_cast<__nv_bfloat16*>(ws + off1);
+  p.ds_scr = reinterpret_cast<__nv_bfloat16*>(ws + off1 + scr);
+  switch (a->head_dim) {
+    case 64: return launch_bwd<64>(p, stream);
+    case 128: return launch_bwd<128>(p, stream);
+    default: return launch_bwd<288>(p, stream);
+  }
+}

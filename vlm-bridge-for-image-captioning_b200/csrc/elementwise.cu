@@ -1,0 +1,371 @@
+// HBM-bound row kernels of the bridge: LayerNorm forward / backward, column reductions for the
+// bias and LayerNorm-affine gradients, fp32 -> bf16 casts (weights, residual-stream gradients with
+// the dropout-backward mask). All are vectorised (16-byte accesses) and coalesced; none reuses data
+// beyond a row, so they use registers rather than shared memory.
+//
+// Reference arithmetic: nn.LayerNorm(2304) (bridge_module.py:282,288,298 / calls :316,326,331),
+// autograd of the same, bias gradients of every nn.Linear, autocast's fp32->bf16 casts.
+#include "common.cuh"
+#include "launch.h"
+
+namespace b200b {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward: one warp per row, the row cached in registers (NV float4 per lane)
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta,
+                                                            __nv_bfloat16* __restrict__ y,
+                                                            float* __restrict__ mean_out,
+                                                            float* __restrict__ rstd_out, int rows, int dim,
+                                                            float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * dim;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < dim) {
+      v[i] = *reinterpret_cast<const float4*>(xr + c);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float mean = warp_sum(s) / (float)dim;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < dim) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)dim + eps);
+  if (lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+  __nv_bfloat16* yr = y + (size_t)row * dim;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < dim) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      uint2 o;
+      o.x = pack_bf16((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+      o.y = pack_bf16((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+      *reinterpret_cast<uint2*>(yr + c) = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward (input gradient): dx = dres + rstd * (g - mean(g) - xhat * mean(g * xhat)),
+// g = dy * gamma. One warp per row; x and dy cached in registers.
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                            const float* __restrict__ x,
+                                                            const float* __restrict__ mean_in,
+                                                            const float* __restrict__ rstd_in,
+                                                            const float* __restrict__ gamma,
+                                                            const float* dres, float* dx, int rows, int dim) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * dim;
+  const __nv_bfloat16* dyr = dy + (size_t)row * dim;
+  const float mean = mean_in[row], rstd = rstd_in[row];
+  float4 xh[NV];  // xhat
+  float4 g[NV];   // dy * gamma
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < dim) {
+      const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+      const uint2 d = *reinterpret_cast<const uint2*>(dyr + c);
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+      g[i] = make_float4(bf16_lo(d.x) * gm.x, bf16_hi(d.x) * gm.y, bf16_lo(d.y) * gm.z, bf16_hi(d.y) * gm.w);
+      s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+    }
+  }
+  const float m1 = warp_sum(s1) / (float)dim;
+  const float m2 = warp_sum(s2) / (float)dim;
+  float* dxr = dx + (size_t)row * dim;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < dim) {
+      float4 o = make_float4(rstd * (g[i].x - m1 - xh[i].x * m2), rstd * (g[i].y - m1 - xh[i].y * m2),
+                             rstd * (g[i].z - m1 - xh[i].z * m2), rstd * (g[i].w - m1 - xh[i].w * m2));
+      if (dres != nullptr) {
+        const float4 r = *reinterpret_cast<const float4*>(dres + (size_t)row * dim + c);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      *reinterpret_cast<float4*>(dxr + c) = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column reductions over rows of a bf16 matrix dy[rows, cols] (pitch ld):
+//   sum[c]   = sum_r dy[r,c]                       (bias gradients, LayerNorm dbeta)
+//   gsum[c]  = sum_r dy[r,c] * (x[r,c]-mean[r])*rstd[r]   (LayerNorm dgamma; only if x != NULL)
+// Block = 32 column-threads (4 columns each, 8-byte loads -> 256 B per warp row) x 8 row-threads.
+// Grid = (col blocks, row chunks); partials go to a workspace and a second kernel sums the chunks
+// in a fixed order (deterministic, no atomics).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16* __restrict__ dy, long long ld,
+                                                             const float* __restrict__ x,
+                                                             const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, float* __restrict__ psum,
+                                                             float* __restrict__ pgsum, int rows, int cols,
+                                                             int rows_per_chunk) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + tx) * 4;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(rows, r0 + rows_per_chunk);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), gs = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < cols) {
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const uint2 d = *reinterpret_cast<const uint2*>(dy + (size_t)r * ld + c);
+      const float d0 = bf16_lo(d.x), d1 = bf16_hi(d.x), d2 = bf16_lo(d.y), d3 = bf16_hi(d.y);
+      s.x += d0; s.y += d1; s.z += d2; s.w += d3;
+      if (x != nullptr) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)r * cols + c);
+        const float m = mean[r], rs = rstd[r];
+        gs.x += d0 * (xv.x - m) * rs; gs.y += d1 * (xv.y - m) * rs;
+        gs.z += d2 * (xv.z - m) * rs; gs.w += d3 * (xv.w - m) * rs;
+      }
+    }
+  }
+  __shared__ float4 sh[2][8][32];
+  sh[0][ty][tx] = s;
+  sh[1][ty][tx] = gs;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+      const float4 a = sh[0][j][tx], b = sh[1][j][tx];
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      gs.x += b.x; gs.y += b.y; gs.z += b.z; gs.w += b.w;
+    }
+    *reinterpret_cast<float4*>(psum + (size_t)blockIdx.y * cols + c) = s;
+    if (x != nullptr) *reinterpret_cast<float4*>(pgsum + (size_t)blockIdx.y * cols + c) = gs;
+  }
+}
+
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ psum,
+                                                           const float* __restrict__ pgsum, float* __restrict__ out_sum,
+                                                           float* __restrict__ out_gsum, int cols, int chunks) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f, g = 0.f;
+  for (int j = 0; j < chunks; ++j) {
+    s += psum[(size_t)j * cols + c];
+    if (pgsum != nullptr) g += pgsum[(size_t)j * cols + c];
+  }
+  if (out_sum != nullptr) out_sum[c] = s;
+  if (out_gsum != nullptr) out_gsum[c] = g;
+}
+
+static int colsum_chunks(int rows, int cols, int num_sms) {
+  const int col_blocks = (cols + 127) / 128;
+  int chunks = (2 * num_sms + col_blocks - 1) / col_blocks;
+  const int max_chunks = (rows + 31) / 32;  // at least 32 rows per chunk
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks > 64) chunks = 64;
+  if (chunks < 1) chunks = 1;
+  return chunks;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> bf16 cast of a contiguous range, optionally applying a dropout-backward mask
+// (element i of `stream` kept iff forward kept it; kept values are scaled by 1/(1-p) after the
+// bf16 rounding, as autograd does on the bf16 gradient).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                        long long n8, DropoutCfg drop, uint32_t stream) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n8; g += stride) {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(in) + 2 * g);
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(in) + 2 * g + 1);
+    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (drop.thr != 0) {
+      const uint4 bits = dropout_bits8(drop, stream, (uint64_t)g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        f[i] = dropout_keep(bits, i, drop.thr) ? bf16_round(bf16_round(f[i]) * drop.scale) : 0.0f;
+    }
+    uint4 o;
+    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+    o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+    reinterpret_cast<uint4*>(out)[g] = o;
+  }
+}
+
+template <typename K, typename... Args>
+static int launch_rows(K kern, int rows, cudaStream_t stream, const char* what, Args... args) {
+  const int warps = 8;
+  const int grid = (rows + warps - 1) / warps;
+  kern<<<grid, warps * 32, 0, stream>>>(args...);
+  return check_launch(what);
+}
+
+}  // namespace b200b
+
+using namespace b200b;
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+#define B200B_DISPATCH_NV(dim, CALL)                                   \
+  do {                                                                 \
+    const int nv_ = ((dim) + 127) / 128;                               \
+    if (nv_ <= 1) { CALL(1); }                                         \
+    else if (nv_ <= 2) { CALL(2); }                                    \
+    else if (nv_ <= 4) { CALL(4); }                                    \
+    else if (nv_ <= 8) { CALL(8); }                                    \
+    else if (nv_ <= 18) { CALL(18); }                                  \
+    else if (nv_ <= 32) { CALL(32); }                                  \
+    else {                                                             \
+      set_last_error("layernorm: dim %d > 4096 not supported", (dim)); \
+      return B200B_ERR_SHAPE;                                          \
+    }                                                                  \
+  } while (0)
+
+extern "C" int b200b_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* mean,
+                                   float* rstd, int rows, int dim, float eps, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !gamma || !beta || !y_bf16 || !mean || !rstd) {
+    set_last_error("layernorm_fwd: null argument");
+    return B200B_ERR_ARG;
+  }
+  if (rows <= 0 || dim <= 0 || (dim % 4) != 0) {
+    set_last_error("layernorm_fwd: need rows > 0 and dim %% 4 == 0 (rows=%d dim=%d)", rows, dim);
+    return B200B_ERR_SHAPE;
+  }
+  if (!al16(x) || !al16(gamma) || !al16(beta) || (reinterpret_cast<uintptr_t>(y_bf16) & 7)) {
+    set_last_error("layernorm_fwd: misaligned pointer");
+    return B200B_ERR_ALIGN;
+  }
+#define CALL(NV)                                                                                              \
+  return launch_rows(layernorm_fwd_kernel<NV>, rows, stream, "layernorm_fwd", x, gamma, beta,                 \
+                     reinterpret_cast<__nv_bfloat16*>(y_bf16), mean, rstd, rows, dim, eps)
+  B200B_DISPATCH_NV(dim, CALL);
+#undef CALL
+  return B200B_OK;
+}
+
+extern "C" int b200b_layernorm_bwd(const void* dy_bf16, const float* x, const float* mean, const float* rstd,
+                                   const float* gamma, const float* dres, float* dx, int rows, int dim,
+                                   void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!dy_bf16 || !x || !mean || !rstd || !gamma || !dx) {
+    set_last_error("layernorm_bwd: null argument");
+    return B200B_ERR_ARG;
+  }
+  if (rows <= 0 || dim <= 0 || (dim % 4) != 0) {
+    set_last_error("layernorm_bwd: need rows > 0 and dim %% 4 == 0 (rows=%d dim=%d)", rows, dim);
+    return B200B_ERR_SHAPE;
+  }
+  if (!al16(x) || !al16(gamma) || !al16(dx) || (dres && !al16(dres)) || (reinterpret_cast<uintptr_t>(dy_bf16) & 7)) {
+    set_last_error("layernorm_bwd: misaligned pointer");
+    return B200B_ERR_ALIGN;
+  }
+#define CALL(NV)                                                                                              \
+  return launch_rows(layernorm_bwd_kernel<NV>, rows, stream, "layernorm_bwd",                                 \
+                     reinterpret_cast<const __nv_bfloat16*>(dy_bf16), x, mean, rstd, gamma, dres, dx, rows, dim)
+  B200B_DISPATCH_NV(dim, CALL);
+#undef CALL
+  return B200B_OK;
+}
+
+extern "C" size_t b200b_colsum_workspace_bytes(int rows, int cols) {
+  // sized for the largest chunk count colsum_chunks() can pick (64), both partial arrays
+  (void)rows;
+  return (size_t)2 * 64 * (size_t)cols * sizeof(float);
+}
+
+extern "C" int b200b_colsum(const void* dy_bf16, int64_t ld, const float* x, const float* mean, const float* rstd,
+                            float* out_sum, float* out_gsum, int rows, int cols, void* workspace, size_t ws_bytes,
+                            void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!dy_bf16 || (!out_sum && !out_gsum) || !workspace) {
+    set_last_error("colsum: null argument");
+    return B200B_ERR_ARG;
+  }
+  if (x != nullptr && (!mean || !rstd || !out_gsum)) {
+    set_last_error("colsum: LayerNorm mode needs x, mean, rstd and out_gsum");
+    return B200B_ERR_ARG;
+  }
+  if (rows <= 0 || cols <= 0 || (cols % 4) != 0 || (ld % 4) != 0) {
+    set_last_error("colsum: need rows > 0, cols %% 4 == 0, ld %% 4 == 0 (rows=%d cols=%d ld=%lld)", rows, cols,
+                   (long long)ld);
+    return B200B_ERR_SHAPE;
+  }
+  if ((reinterpret_cast<uintptr_t>(dy_bf16) & 7) || (x && !al16(x)) || !al16(workspace)) {
+    set_last_error("colsum: misaligned pointer");
+    return B200B_ERR_ALIGN;
+  }
+  int num_sms = 0;
+  int rc = device_sm_count(&num_sms);
+  if (rc != B200B_OK) return rc;
+  const int chunks = colsum_chunks(rows, cols, num_sms);
+  if (ws_bytes < (size_t)2 * chunks * cols * sizeof(float)) {
+    set_last_error("colsum: workspace too small (%zu < %zu)", ws_bytes, (size_t)2 * chunks * cols * sizeof(float));
+    return B200B_ERR_WORKSPACE;
+  }
+  float* psum = reinterpret_cast<float*>(workspace);
+  float* pgsum = psum + (size_t)chunks * cols;
+  const int rows_per_chunk = (rows + chunks - 1) / chunks;
+  dim3 grid((cols + 127) / 128, chunks);
+  colsum_partial_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16), (long long)ld, x,
+                                                  mean, rstd, psum, pgsum, rows, cols, rows_per_chunk);
+  rc = check_launch("colsum_partial");
+  if (rc != B200B_OK) return rc;
+  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(psum, x ? pgsum : nullptr, out_sum, out_gsum, cols,
+                                                              chunks);
+  return check_launch("colsum_final");
+}
+
+extern "C" int b200b_cast_bf16(const float* in, void* out_bf16, int64_t n, float dropout_p, uint64_t seed,
+                               uint32_t dropout_stream, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!in || !out_bf16) {
+    set_last_error("cast_bf16: null argument");
+    return B200B_ERR_ARG;
+  }
+  if (n <= 0 || (n % 8) != 0) {
+    set_last_error("cast_bf16: n must be a positive multiple of 8 (n=%lld)", (long long)n);
+    return B200B_ERR_SHAPE;
+  }
+  if (!al16(in) || !al16(out_bf16)) {
+    set_last_error("cast_bf16: misaligned pointer");
+    return B200B_ERR_ALIGN;
+  }
+  if (!(dropout_p >= 0.0f && dropout_p < 1.0f)) {
+    set_last_error("cast_bf16: dropout_p must be in [0,1)");
+    return B200B_ERR_ARG;
+  }
+  int num_sms = 0;
+  int rc = device_sm_count(&num_sms);
+  if (rc != B200B_OK) return rc;
+  const long long n8 = n / 8;
+  long long blocks = (n8 + 255) / 256;
+  const long long cap = (long long)num_sms * 8;  // 8 resident CTAs of 256 threads per SM, grid-stride beyond
+  if (blocks > cap) blocks = cap;
+  cast_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out_bf16), n8,
+                                                    make_dropout_cfg(dropout_p, seed), dropout_stream);
+  return check_launch("cast_bf16");
+}

@@ -64,3 +64,101 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_major: int = 0, b_major: int = 0
     if epilogue == EPI_BF16_BIAS_GELU:
         return out, aux
     return out
+
+
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5):
+    """x f32 [rows, dim] -> (y bf16, mean f32[rows], rstd f32[rows])."""
+    _need_cuda(x, gamma, beta)
+    rows, dim = x.shape
+    y = torch.empty((rows, dim), device=x.device, dtype=torch.bfloat16)
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200b_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                              mean.data_ptr(), rstd.data_ptr(), rows, dim, eps, _stream_ptr()),
+               "layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor,
+                  gamma: torch.Tensor, dres: torch.Tensor | None = None, out: torch.Tensor | None = None):
+    """dx f32 = dres + LN-backward(dy bf16)."""
+    _need_cuda(dy, x, mean, rstd, gamma, dres, out)
+    rows, dim = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_lib.lib().b200b_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                              gamma.data_ptr(), _ptr(dres), out.data_ptr(), rows, dim,
+                                              _stream_ptr()), "layernorm_bwd")
+    return out
+
+
+def colsum(dy: torch.Tensor, *, x: torch.Tensor | None = None, mean: torch.Tensor | None = None,
+           rstd: torch.Tensor | None = None, out_sum: torch.Tensor | None = None,
+           out_gsum: torch.Tensor | None = None, workspace: torch.Tensor | None = None):
+    """Column sums of dy bf16 [rows, cols] (and the LayerNorm dgamma sums when x is given)."""
+    _need_cuda(dy, x, out_sum, out_gsum)
+    rows, cols = dy.shape
+    if out_sum is None:
+        out_sum = torch.empty(cols, device=dy.device, dtype=torch.float32)
+    if x is not None and out_gsum is None:
+        out_gsum = torch.empty(cols, device=dy.device, dtype=torch.float32)
+    nbytes = _lib.lib().b200b_colsum_workspace_bytes(rows, cols)
+    if workspace is None:
+        workspace = torch.empty(nbytes, device=dy.device, dtype=torch.uint8)
+    _lib.check(_lib.lib().b200b_colsum(dy.data_ptr(), dy.stride(0), _ptr(x), _ptr(mean), _ptr(rstd),
+                                       out_sum.data_ptr(), _ptr(out_gsum), rows, cols, workspace.data_ptr(),
+                                       workspace.numel(), _stream_ptr()), "colsum")
+    return (out_sum, out_gsum) if x is not None else out_sum
+
+
+def cast_bf16(x: torch.Tensor, out: torch.Tensor | None = None, dropout_p: float = 0.0, seed: int = 0,
+              dropout_stream: int = 0) -> torch.Tensor:
+    _need_cuda(x, out)
+    if not x.is_contiguous() or x.dtype != torch.float32:
+        raise RuntimeError("cast_bf16 needs a contiguous fp32 tensor")
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().b200b_cast_bf16(x.data_ptr(), out.data_ptr(), x.numel(), dropout_p, seed,
+                                          dropout_stream, _stream_ptr()), "cast_bf16")
+    return out
+
+
+def _attn_args(q, k, v, o, lse, batch, heads, len_q, len_k, head_dim, dropout_p, seed, dropout_stream):
+    return _lib.AttnArgs(q=q.data_ptr(), ldq=q.stride(0), k=k.data_ptr(), ldk=k.stride(0),
+                         v=v.data_ptr(), ldv=v.stride(0), o=o.data_ptr(), ldo=o.stride(0),
+                         lse=lse.data_ptr(), batch=batch, heads=heads, len_q=len_q, len_k=len_k,
+                         head_dim=head_dim, dropout_p=dropout_p, seed=seed, dropout_stream=dropout_stream,
+                         reserved=0)
+
+
+def attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, batch: int, heads: int,
+                  len_q: int, len_k: int, head_dim: int, dropout_p: float = 0.0, seed: int = 0,
+                  dropout_stream: int = 0, out: torch.Tensor | None = None):
+    """q: [batch*len_q, >=heads*head_dim] bf16 (2-D view, any row pitch); k, v: [batch*len_k, ...].
+
+    Returns (o bf16 [batch*len_q, heads*head_dim], lse f32 [batch, heads, len_q])."""
+    _need_cuda(q, k, v, out)
+    if out is None:
+        out = torch.empty((batch * len_q, heads * head_dim), device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty((batch, heads, len_q), device=q.device, dtype=torch.float32)
+    args = _attn_args(q, k, v, out, lse, batch, heads, len_q, len_k, head_dim, dropout_p, seed, dropout_stream)
+    _lib.check(_lib.lib().b200b_attention_fwd(C.byref(args), _stream_ptr()), "attention_fwd")
+    return out, lse
+
+
+def attention_bwd(d_o: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor,
+                  lse: torch.Tensor, dq: torch.Tensor, dk: torch.Tensor, dv: torch.Tensor, *, batch: int,
+                  heads: int, len_q: int, len_k: int, head_dim: int, dropout_p: float = 0.0, seed: int = 0,
+                  dropout_stream: int = 0, workspace: torch.Tensor | None = None) -> None:
+    """Writes dq / dk / dv (bf16 2-D views, any row pitch)."""
+    _need_cuda(d_o, q, k, v, o, lse, dq, dk, dv)
+    nbytes = _lib.lib().b200b_attention_bwd_workspace_bytes(batch, heads, len_q, len_k)
+    if workspace is None:
+        workspace = torch.empty(nbytes, device=q.device, dtype=torch.uint8)
+    args = _attn_args(q, k, v, o, lse, batch, heads, len_q, len_k, head_dim, dropout_p, seed, dropout_stream)
+    args.d_o, args.lddo = d_o.data_ptr(), d_o.stride(0)
+    args.dq, args.lddq = dq.data_ptr(), dq.stride(0)
+    args.dk, args.lddk = dk.data_ptr(), dk.stride(0)
+    args.dv, args.lddv = dv.data_ptr(), dv.stride(0)
+    args.workspace, args.workspace_bytes = workspace.data_ptr(), workspace.numel()
+    _lib.check(_lib.lib().b200b_attention_bwd(C.byref(args), _stream_ptr()), "attention_bwd")
