@@ -156,6 +156,82 @@ int b200b_attention_fwd(const b200b_attn_args* args, void* stream);
 size_t b200b_attention_bwd_workspace_bytes(int batch, int heads, int len_q, int len_k);
 int b200b_attention_bwd(const b200b_attn_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------- *
+ * Whole-block entry points: one call enqueues every kernel of a BridgeBlock forward or backward
+ * (reference: BridgeBlock.forward, bridge_module.py:300-335, and the autograd graph it builds).
+ * The host loop over blocks (BridgeLite.forward, :438-442) stays in Python so that the per-block
+ * debug statistics (:427-454) and the data-parallel gradient buckets can be interleaved.
+ *
+ * T = batch*len_text text rows, Tv = batch*len_vision vision rows, D = dim, Dv = dim_vision,
+ * F = dim_ffn, nb = num_blocks. All weights are bf16 copies of the fp32 masters in nn.Linear
+ * layout [out_features, in_features]; biases / LayerNorm affine stay fp32.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct b200b_bridge_dims {
+  int32_t batch, len_text, len_vision;
+  int32_t dim, dim_vision, dim_ffn;
+  int32_t heads_cross, heads_self;
+  int32_t num_blocks;
+  int32_t reserved;
+} b200b_bridge_dims;
+
+typedef struct b200b_block_weights {
+  const void* wq_c;   /* bf16 [D, D]    cross_attention.w_q.weight                         */
+  const void* wo_c;   /* bf16 [D, D]    cross_attention.w_o.weight                         */
+  const void* wqkv_s; /* bf16 [3D, D]   self_attention.w_q | w_k | w_v .weight, stacked    */
+  const void* wo_s;   /* bf16 [D, D]    self_attention.w_o.weight                          */
+  const void* w1;     /* bf16 [F, D]    ffn.0.weight                                       */
+  const void* w2;     /* bf16 [D, F]    ffn.3.weight                                       */
+  const float* bq_c;  /* f32 [D]  */
+  const float* bo_c;  /* f32 [D]  */
+  const float* bqkv_s;/* f32 [3D] */
+  const float* bo_s;  /* f32 [D]  */
+  const float* b1;    /* f32 [F]  */
+  const float* b2;    /* f32 [D]  */
+  const float* ln_c_g; const float* ln_c_b; /* ln_cross  */
+  const float* ln_s_g; const float* ln_s_b; /* ln_self   */
+  const float* ln_f_g; const float* ln_f_b; /* ln_ffn    */
+} b200b_block_weights;
+
+/* fp32 gradient destinations of one block, same shapes as the weights above */
+typedef struct b200b_block_grads {
+  float* wq_c; float* wo_c; float* wqkv_s; float* wo_s; float* w1; float* w2;
+  float* bq_c; float* bo_c; float* bqkv_s; float* bo_s; float* b1; float* b2;
+  float* ln_c_g; float* ln_c_b; float* ln_s_g; float* ln_s_b; float* ln_f_g; float* ln_f_b;
+} b200b_block_grads;
+
+/* bytes of the per-block activation arena written by block_forward and read by block_backward */
+size_t b200b_bridge_block_saved_bytes(const b200b_bridge_dims* dims);
+/* bytes of the transient workspace of block_backward / kv_backward */
+size_t b200b_bridge_backward_workspace_bytes(const b200b_bridge_dims* dims);
+
+/* Vision K/V for all blocks at once (bridge_module.py:99-100; computed once per image and reused by
+ * every block and, in decode, by every step -- SURVEY.md 8a row a12):
+ *   vision_bf16 [Tv, Dv] = bf16(vision_f32);  kv [Tv, nb*2D] = vision_bf16 @ wkv_all^T + bkv_all
+ * wkv_all bf16 [nb*2D, Dv] = (w_k, w_v) of block 0, then block 1, ...; block i's K is columns
+ * [2iD, 2iD+D) of kv and its V the next D columns. */
+int b200b_bridge_kv_project(const b200b_bridge_dims* dims, const float* vision_f32,
+                            const void* wkv_all, const float* bkv_all, void* vision_bf16,
+                            void* kv, void* stream);
+
+/* x_out f32 [T, D] = BridgeBlock(x_in f32 [T, D], kv). dropout_p > 0 only in training mode. */
+int b200b_bridge_block_forward(const b200b_bridge_dims* dims, int block_index,
+                               const b200b_block_weights* w, const float* x_in, const void* kv,
+                               float* x_out, void* saved, size_t saved_bytes, float dropout_p,
+                               uint64_t seed, void* stream);
+
+/* Backward of one block. d_out f32 [T, D] is the gradient of x_out; writes every field of `g`,
+ * the block's columns of dkv bf16 [Tv, nb*2D], and (if d_in != NULL) d_in f32 [T, D]. */
+int b200b_bridge_block_backward(const b200b_bridge_dims* dims, int block_index,
+                                const b200b_block_weights* w, const float* x_in, const void* kv,
+                                const void* saved, const float* d_out, float* d_in, void* dkv,
+                                const b200b_block_grads* g, void* workspace, size_t workspace_bytes,
+                                float dropout_p, uint64_t seed, void* stream);
+
+/* dwkv_all f32 [nb*2D, Dv] = dkv^T @ vision_bf16 ; dbkv_all f32 [nb*2D] = column sums of dkv */
+int b200b_bridge_kv_backward(const b200b_bridge_dims* dims, const void* vision_bf16,
+                             const void* dkv, float* dwkv_all, float* dbkv_all, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,3 +3,6 @@
 Reference: src/vlm_bridge/model_architecture/bridge_module.py (BridgeLite and its blocks).
 """
 __version__ = "0.1.0"
+
+from .bridge import (BridgeBlock, BridgeLite, MultiHeadCrossAttention,  # noqa: E402,F401
+                     MultiHeadSelfAttention)

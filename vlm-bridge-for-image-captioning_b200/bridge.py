@@ -1,0 +1,533 @@
+"""Drop-in `BridgeLite` whose forward/backward run on the sm_100a kernels of libb200_bridge.so.
+
+Mirrors the reference module surface (src/vlm_bridge/model_architecture/bridge_module.py):
+  * constructor `(vision_dim, language_dim, num_blocks, num_heads_cross, num_heads_self, dropout)`
+    (:350-358), attributes `vision_dim / language_dim / num_blocks / bridge_blocks` (:372-389);
+  * `forward(vision_features, text_embeddings, debug=False)` (:406-456) and `get_model_info()`
+    (:458-471);
+  * the 52-tensor `state_dict` layout and parameter registration order,
+    Xavier-uniform / zero-bias / unit-LayerNorm init consuming the torch RNG exactly like the
+    reference (:394-404), so `torch.manual_seed(s); BridgeLite()` yields identical weights.
+
+What differs is only *how* the arithmetic runs: parameters live in one flat fp32 buffer (each
+`nn.Parameter` is a view of it), a bf16 copy of the weight region is refreshed when a parameter
+version changes, and one `torch.autograd.Function` enqueues whole-block CUDA entry points. Math is
+bf16-operand / fp32-accumulate with an fp32 residual stream, i.e. the reference's numerics under
+`torch.autocast(dtype=bfloat16)`, whether or not autocast is active.
+There is no CPU or eager-PyTorch fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+__all__ = ["BridgeLite", "BridgeBlock", "MultiHeadCrossAttention", "MultiHeadSelfAttention"]
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers: same attribute names / construction order as the reference classes so the
+# state_dict keys, registration order and RNG consumption at init are identical
+# ------------------------------------------------------------------------------------------------
+class MultiHeadCrossAttention(nn.Module):
+    """Parameter container of the cross-attention (reference bridge_module.py:24-73)."""
+
+    def __init__(self, query_dim: int, kv_dim: int, d_model: int, num_heads: int = 8, dropout: float = 0.2):
+        super().__init__()
+        assert d_model % num_heads == 0
+        self.query_dim, self.kv_dim, self.d_model, self.num_heads = query_dim, kv_dim, d_model, num_heads
+        self.d_k = d_model // num_heads
+        self.w_q = nn.Linear(query_dim, d_model)
+        self.w_k = nn.Linear(kv_dim, d_model)
+        self.w_v = nn.Linear(kv_dim, d_model)
+        self.w_o = nn.Linear(d_model, query_dim)
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, *args, **kwargs):  # pragma: no cover - guidance only
+        raise RuntimeError("the B200 bridge fuses its sub-layers; call BridgeLite.forward (no per-layer path)")
+
+
+class MultiHeadSelfAttention(nn.Module):
+    """Parameter container of the self-attention (reference bridge_module.py:142-176)."""
+
+    def __init__(self, d_model: int, num_heads: int = 18, dropout: float = 0.2):
+        super().__init__()
+        assert d_model % num_heads == 0
+        self.d_model, self.num_heads = d_model, num_heads
+        self.d_k = d_model // num_heads
+        self.w_q = nn.Linear(d_model, d_model)
+        self.w_k = nn.Linear(d_model, d_model)
+        self.w_v = nn.Linear(d_model, d_model)
+        self.w_o = nn.Linear(d_model, d_model)
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, *args, **kwargs):  # pragma: no cover - guidance only
+        raise RuntimeError("the B200 bridge fuses its sub-layers; call BridgeLite.forward (no per-layer path)")
+
+
+class BridgeBlock(nn.Module):
+    """Parameter container of one block (reference bridge_module.py:240-298)."""
+
+    def __init__(self, vision_dim: int = 1024, language_dim: int = 2304, num_heads_cross: int = 8,
+                 num_heads_self: int = 18, dropout: float = 0.2):
+        super().__init__()
+        self.vision_dim, self.language_dim = vision_dim, language_dim
+        self.cross_attention = MultiHeadCrossAttention(query_dim=language_dim, kv_dim=vision_dim,
+                                                       d_model=language_dim, num_heads=num_heads_cross,
+                                                       dropout=dropout)
+        self.ln_cross = nn.LayerNorm(language_dim)
+        self.self_attention = MultiHeadSelfAttention(d_model=language_dim, num_heads=num_heads_self,
+                                                     dropout=dropout)
+        self.ln_self = nn.LayerNorm(language_dim)
+        self.ffn = nn.Sequential(
+            nn.Linear(language_dim, language_dim * 4),
+            nn.GELU(),
+            nn.Dropout(dropout),
+            nn.Linear(language_dim * 4, language_dim),
+            nn.Dropout(dropout),
+        )
+        self.ln_ffn = nn.LayerNorm(language_dim)
+
+    def forward(self, *args, **kwargs):  # pragma: no cover - guidance only
+        raise RuntimeError("the B200 bridge fuses its sub-layers; call BridgeLite.forward (no per-layer path)")
+
+
+# ------------------------------------------------------------------------------------------------
+# flat parameter layout
+# ------------------------------------------------------------------------------------------------
+class _Layout:
+    """Element offsets of every parameter inside the flat fp32 buffer.
+
+    Region W (2-D weights, mirrored 1:1 into the bf16 arena):
+        [ (w_k, w_v) of block 0, block 1, ... ]                      -> one [nb*2D, Dv] matrix
+        per block: cross w_q | cross w_o | self w_q,w_k,w_v ([3D,D]) | self w_o | ffn.0 | ffn.3
+    Region V (vectors, fp32 only):
+        [ (b_k, b_v) of block 0, block 1, ... ]                      -> one [nb*2D] vector
+        per block: cross b_q | cross b_o | self b_q,b_k,b_v ([3D]) | self b_o | ffn.0.b | ffn.3.b |
+                   ln_cross w,b | ln_self w,b | ln_ffn w,b
+    The gradient arena uses the same offsets, so a block's gradients are two contiguous slabs
+    (its W slab and its V slab) -- the data-parallel buckets.
+    """
+
+    def __init__(self, nb: int, D: int, Dv: int, F: int):
+        self.nb, self.D, self.Dv, self.F = nb, D, Dv, F
+        self.offsets: dict[str, int] = {}
+        off = 0
+
+        def put(name: str, n: int) -> None:
+            nonlocal off
+            self.offsets[name] = off
+            off += n
+
+        self.kv_w_start = off
+        for i in range(nb):
+            put(f"bridge_blocks.{i}.cross_attention.w_k.weight", D * Dv)
+            put(f"bridge_blocks.{i}.cross_attention.w_v.weight", D * Dv)
+        self.block_w_start, self.block_w_end = [], []
+        for i in range(nb):
+            self.block_w_start.append(off)
+            pre = f"bridge_blocks.{i}."
+            put(pre + "cross_attention.w_q.weight", D * D)
+            put(pre + "cross_attention.w_o.weight", D * D)
+            put(pre + "self_attention.w_q.weight", D * D)
+            put(pre + "self_attention.w_k.weight", D * D)
+            put(pre + "self_attention.w_v.weight", D * D)
+            put(pre + "self_attention.w_o.weight", D * D)
+            put(pre + "ffn.0.weight", F * D)
+            put(pre + "ffn.3.weight", D * F)
+            self.block_w_end.append(off)
+        self.n_weights = off
+        self.kv_b_start = off
+        for i in range(nb):
+            put(f"bridge_blocks.{i}.cross_attention.w_k.bias", D)
+            put(f"bridge_blocks.{i}.cross_attention.w_v.bias", D)
+        self.block_v_start, self.block_v_end = [], []
+        for i in range(nb):
+            self.block_v_start.append(off)
+            pre = f"bridge_blocks.{i}."
+            put(pre + "cross_attention.w_q.bias", D)
+            put(pre + "cross_attention.w_o.bias", D)
+            put(pre + "self_attention.w_q.bias", D)
+            put(pre + "self_attention.w_k.bias", D)
+            put(pre + "self_attention.w_v.bias", D)
+            put(pre + "self_attention.w_o.bias", D)
+            put(pre + "ffn.0.bias", F)
+            put(pre + "ffn.3.bias", D)
+            for ln in ("ln_cross", "ln_self", "ln_ffn"):
+                put(pre + ln + ".weight", D)
+                put(pre + ln + ".bias", D)
+            self.block_v_end.append(off)
+        self.total = off
+
+    def buckets(self) -> list[tuple[int, int]]:
+        """(start, end) element ranges in the order backward finishes them (last block first)."""
+        out = []
+        for i in reversed(range(self.nb)):
+            out.append((self.block_w_start[i], self.block_w_end[i]))
+            out.append((self.block_v_start[i], self.block_v_end[i]))
+        out.append((self.kv_w_start, self.block_w_start[0]))
+        out.append((self.kv_b_start, self.block_v_start[0]))
+        return out
+
+
+class _BridgeDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("batch", "len_text", "len_vision", "dim", "dim_vision", "dim_ffn",
+                                         "heads_cross", "heads_self", "num_blocks", "reserved")]
+
+
+_W_FIELDS = ["wq_c", "wo_c", "wqkv_s", "wo_s", "w1", "w2", "bq_c", "bo_c", "bqkv_s", "bo_s", "b1", "b2",
+             "ln_c_g", "ln_c_b", "ln_s_g", "ln_s_b", "ln_f_g", "ln_f_b"]
+_W_KEYS = ["cross_attention.w_q.weight", "cross_attention.w_o.weight", "self_attention.w_q.weight",
+           "self_attention.w_o.weight", "ffn.0.weight", "ffn.3.weight", "cross_attention.w_q.bias",
+           "cross_attention.w_o.bias", "self_attention.w_q.bias", "self_attention.w_o.bias", "ffn.0.bias",
+           "ffn.3.bias", "ln_cross.weight", "ln_cross.bias", "ln_self.weight", "ln_self.bias", "ln_ffn.weight",
+           "ln_ffn.bias"]
+
+
+class _BlockPtrs(C.Structure):
+    """b200b_block_weights and b200b_block_grads share this shape (18 pointers)."""
+    _fields_ = [(n, C.c_void_p) for n in _W_FIELDS]
+
+
+def _declare_bridge(lib) -> None:
+    if getattr(lib, "_b200b_bridge_declared", False):
+        return
+    P = C.POINTER
+    lib.b200b_bridge_block_saved_bytes.restype = C.c_size_t
+    lib.b200b_bridge_block_saved_bytes.argtypes = [P(_BridgeDims)]
+    lib.b200b_bridge_backward_workspace_bytes.restype = C.c_size_t
+    lib.b200b_bridge_backward_workspace_bytes.argtypes = [P(_BridgeDims)]
+    lib.b200b_bridge_kv_project.restype = C.c_int
+    lib.b200b_bridge_kv_project.argtypes = [P(_BridgeDims)] + [C.c_void_p] * 6
+    lib.b200b_bridge_block_forward.restype = C.c_int
+    lib.b200b_bridge_block_forward.argtypes = [P(_BridgeDims), C.c_int, P(_BlockPtrs), C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_uint64,
+                                               C.c_void_p]
+    lib.b200b_bridge_block_backward.restype = C.c_int
+    lib.b200b_bridge_block_backward.argtypes = [P(_BridgeDims), C.c_int, P(_BlockPtrs), C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, P(_BlockPtrs),
+                                                C.c_void_p, C.c_size_t, C.c_float, C.c_uint64, C.c_void_p]
+    lib.b200b_bridge_kv_backward.restype = C.c_int
+    lib.b200b_bridge_kv_backward.argtypes = [P(_BridgeDims), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_size_t, C.c_void_p]
+    lib._b200b_bridge_declared = True
+
+
+def _bridge_lib():
+    lib = _lib.lib()
+    _declare_bridge(lib)
+    return lib
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ------------------------------------------------------------------------------------------------
+# the autograd function: one node for the whole bridge
+# ------------------------------------------------------------------------------------------------
+class _BridgeFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module: "BridgeLite", vision: torch.Tensor, text: torch.Tensor, *params: torch.Tensor):
+        out, state = module._run_forward(vision, text, keep_for_backward=True)
+        ctx.module = module
+        ctx.state = state
+        ctx.text_needs_grad = text.requires_grad
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_out: torch.Tensor):
+        module: BridgeLite = ctx.module
+        d_text, grads = module._run_backward(ctx.state, d_out, ctx.text_needs_grad)
+        ctx.state = None
+        return (None, None, d_text, *grads)
+
+
+class BridgeLite(nn.Module):
+    """Bridge-Lite on B200: same constructor, forward signature and state_dict as the reference
+    `BridgeLite` (bridge_module.py:338-471)."""
+
+    def __init__(self, vision_dim: int = 1024, language_dim: int = 2304, num_blocks: int = 2,
+                 num_heads_cross: int = 8, num_heads_self: int = 18, dropout: float = 0.2):
+        super().__init__()
+        self.vision_dim = vision_dim
+        self.language_dim = language_dim
+        self.num_blocks = num_blocks
+        self.num_heads_cross = num_heads_cross
+        self.num_heads_self = num_heads_self
+        self.dropout_p = float(dropout)
+        self.bridge_blocks = nn.ModuleList([
+            BridgeBlock(vision_dim=vision_dim, language_dim=language_dim, num_heads_cross=num_heads_cross,
+                        num_heads_self=num_heads_self, dropout=dropout) for _ in range(num_blocks)
+        ])
+        self._init_weights()
+        self._layout = _Layout(num_blocks, language_dim, vision_dim, language_dim * 4)
+        # lazily built device state (never part of state_dict)
+        self._flat: Optional[torch.Tensor] = None
+        self._w16: Optional[torch.Tensor] = None
+        self._w16_key = None
+        self._ptrs = None
+        # data-parallel hook: called as hook(grad_arena, start, end) when a bucket is final
+        self._bucket_hook: Optional[Callable[[torch.Tensor, int, int], None]] = None
+        self._last_grad_arena: Optional[torch.Tensor] = None
+
+    # -- init exactly as the reference (bridge_module.py:394-404) ---------------------------------
+    def _init_weights(self) -> None:
+        for module in self.modules():
+            if isinstance(module, nn.Linear):
+                nn.init.xavier_uniform_(module.weight)
+                if module.bias is not None:
+                    nn.init.zeros_(module.bias)
+            elif isinstance(module, nn.LayerNorm):
+                nn.init.ones_(module.weight)
+                nn.init.zeros_(module.bias)
+
+    # -- flat parameter storage --------------------------------------------------------------------
+    def _named_params(self) -> list[tuple[str, nn.Parameter]]:
+        return list(self.named_parameters())
+
+    def _ensure_flat(self) -> None:
+        """Make every parameter a view of one flat fp32 CUDA buffer (re-done after .to()/.cuda())."""
+        named = self._named_params()
+        dev = named[0][1].device
+        if dev.type != "cuda":
+            raise RuntimeError("BridgeLite (B200) runs on CUDA only: move the module to a cuda device "
+                               "(there is no CPU fallback)")
+        lay = self._layout
+        flat = self._flat
+        ok = flat is not None and flat.device == dev
+        if ok:
+            base = flat.data_ptr()
+            for name, p in named:
+                if p.dtype != torch.float32 or p.data_ptr() != base + 4 * lay.offsets[name]:
+                    ok = False
+                    break
+        if ok:
+            return
+        for _, p in named:
+            if p.dtype != torch.float32:
+                raise RuntimeError("BridgeLite (B200) keeps fp32 master parameters; do not cast the module "
+                                   "to half precision (bf16 operand copies are made internally)")
+        flat = torch.empty(lay.total, device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            for name, p in named:
+                o = lay.offsets[name]
+                view = flat[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+        self._flat = flat
+        self._w16 = torch.empty(lay.n_weights, device=dev, dtype=torch.bfloat16)
+        self._w16_key = None
+        self._ptrs = None
+
+    def _refresh_bf16(self) -> None:
+        key = tuple(p._version for _, p in self._named_params())
+        if key == self._w16_key:
+            return
+        lay = self._layout
+        _lib.check(_lib.lib().b200b_cast_bf16(self._flat.data_ptr(), self._w16.data_ptr(), lay.n_weights, 0.0, 0, 0,
+                                              _stream()), "cast_bf16(weights)")
+        self._w16_key = key
+
+    def _block_ptr_struct(self, base16: int, base32: int, i: int, grads: bool) -> _BlockPtrs:
+        lay = self._layout
+        s = _BlockPtrs()
+        pre = f"bridge_blocks.{i}."
+        for field, key in zip(_W_FIELDS, _W_KEYS):
+            off = lay.offsets[pre + key]
+            if off < lay.n_weights and not grads:
+                setattr(s, field, base16 + 2 * off)
+            else:
+                setattr(s, field, base32 + 4 * off)
+        return s
+
+    def _weight_ptrs(self):
+        if self._ptrs is None:
+            b16, b32 = self._w16.data_ptr(), self._flat.data_ptr()
+            self._ptrs = [self._block_ptr_struct(b16, b32, i, grads=False) for i in range(self.num_blocks)]
+        return self._ptrs
+
+    def _dims(self, B: int, L: int, Nv: int) -> _BridgeDims:
+        return _BridgeDims(batch=B, len_text=L, len_vision=Nv, dim=self.language_dim, dim_vision=self.vision_dim,
+                           dim_ffn=self.language_dim * 4, heads_cross=self.num_heads_cross,
+                           heads_self=self.num_heads_self, num_blocks=self.num_blocks, reserved=0)
+
+    # -- vision K/V (shared with the decode cache) -------------------------------------------------
+    def project_vision_kv(self, vision_features: torch.Tensor):
+        """K/V of every block for `vision_features` [B, Nv, vision_dim] -> (vision_bf16, kv bf16
+        [B*Nv, num_blocks*2*language_dim]). Reference: bridge_module.py:99-100."""
+        self._ensure_flat()
+        self._refresh_bf16()
+        v = vision_features.detach().to(device=self._flat.device, dtype=torch.float32).contiguous()
+        B, Nv, Dv = v.shape
+        if Dv != self.vision_dim:
+            raise RuntimeError(f"vision_features last dim {Dv} != vision_dim {self.vision_dim}")
+        lay = self._layout
+        D = self.language_dim
+        vb = torch.empty((B * Nv, Dv), device=v.device, dtype=torch.bfloat16)
+        kv = torch.empty((B * Nv, self.num_blocks * 2 * D), device=v.device, dtype=torch.bfloat16)
+        dims = self._dims(B, 1, Nv)
+        _lib.check(_bridge_lib().b200b_bridge_kv_project(
+            C.byref(dims), v.data_ptr(), self._w16.data_ptr() + 2 * lay.kv_w_start,
+            self._flat.data_ptr() + 4 * lay.kv_b_start, vb.data_ptr(), kv.data_ptr(), _stream()), "kv_project")
+        return vb, kv
+
+    # -- forward / backward drivers ----------------------------------------------------------------
+    def _run_forward(self, vision: torch.Tensor, text: torch.Tensor, keep_for_backward: bool, kv_cache=None,
+                     block_callback=None):
+        self._ensure_flat()
+        self._refresh_bf16()
+        dev = self._flat.device
+        if text.device != dev:
+            raise RuntimeError("text_embeddings must be on the module's CUDA device")
+        if text.dim() != 3 or text.shape[-1] != self.language_dim:
+            raise RuntimeError(f"text_embeddings must be [B, L, {self.language_dim}]")
+        x = text.detach().to(torch.float32).contiguous()
+        B, L, D = x.shape
+        if kv_cache is None:
+            if vision.dim() != 3 or vision.shape[0] != B:
+                raise RuntimeError("vision_features must be [B, Nv, vision_dim] with the text batch size")
+            vb, kv = self.project_vision_kv(vision)
+            Nv = vision.shape[1]
+        else:
+            vb, kv, Nv = None, kv_cache.kv, kv_cache.len_vision
+            if kv_cache.batch != B:
+                raise RuntimeError("kv cache batch does not match text batch")
+        lib = _bridge_lib()
+        dims = self._dims(B, L, Nv)
+        saved_bytes = lib.b200b_bridge_block_saved_bytes(C.byref(dims))
+        n_arenas = self.num_blocks if keep_for_backward else 1
+        saved = torch.empty(n_arenas * saved_bytes, device=dev, dtype=torch.uint8)
+        p = self.dropout_p if self.training else 0.0
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
+        ptrs = self._weight_ptrs()
+        xs = [x.view(B * L, D)]
+        st = _stream()
+        for i in range(self.num_blocks):
+            x_out = torch.empty((B * L, D), device=dev, dtype=torch.float32)
+            arena = saved.data_ptr() + (i if keep_for_backward else 0) * saved_bytes
+            _lib.check(lib.b200b_bridge_block_forward(C.byref(dims), i, C.byref(ptrs[i]), xs[-1].data_ptr(),
+                                                      kv.data_ptr(), x_out.data_ptr(), arena, saved_bytes, p, seed,
+                                                      st), "block_forward")
+            if block_callback is not None:
+                block_callback(i, xs[-1].view(B, L, D), x_out.view(B, L, D))
+            xs.append(x_out)
+        out = xs[-1].view(B, L, D)
+        state = None
+        if keep_for_backward:
+            state = dict(dims=dims, saved=saved, saved_bytes=saved_bytes, kv=kv, vb=vb, xs=xs[:-1], p=p, seed=seed,
+                         versions=self._w16_key)
+        return out, state
+
+    def _run_backward(self, state, d_out: torch.Tensor, text_needs_grad: bool):
+        lay = self._layout
+        dev = self._flat.device
+        lib = _bridge_lib()
+        dims = state["dims"]
+        if state["versions"] != tuple(p._version for _, p in self._named_params()):
+            raise RuntimeError("bridge parameters were modified in place between forward and backward")
+        B, L, D = dims.batch, dims.len_text, dims.dim
+        d = d_out.detach().to(torch.float32).contiguous().view(B * L, D)
+        garena = torch.empty(lay.total, device=dev, dtype=torch.float32)
+        gbase = garena.data_ptr()
+        ws_bytes = lib.b200b_bridge_backward_workspace_bytes(C.byref(dims))
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        dkv = torch.empty_like(state["kv"])
+        ptrs = self._weight_ptrs()
+        st = _stream()
+        hook = self._bucket_hook
+        for i in reversed(range(self.num_blocks)):
+            need_din = i > 0 or text_needs_grad
+            d_in = torch.empty((B * L, D), device=dev, dtype=torch.float32) if need_din else None
+            g = self._block_ptr_struct(0, gbase, i, grads=True)
+            arena = state["saved"].data_ptr() + i * state["saved_bytes"]
+            _lib.check(lib.b200b_bridge_block_backward(
+                C.byref(dims), i, C.byref(ptrs[i]), state["xs"][i].data_ptr(), state["kv"].data_ptr(), arena,
+                d.data_ptr(), None if d_in is None else d_in.data_ptr(), dkv.data_ptr(), C.byref(g), ws.data_ptr(),
+                ws_bytes, state["p"], state["seed"], st), "block_backward")
+            if hook is not None:
+                hook(garena, lay.block_w_start[i], lay.block_w_end[i])
+                hook(garena, lay.block_v_start[i], lay.block_v_end[i])
+            d = d_in
+        _lib.check(lib.b200b_bridge_kv_backward(C.byref(dims), state["vb"].data_ptr(), dkv.data_ptr(),
+                                                gbase + 4 * lay.kv_w_start, gbase + 4 * lay.kv_b_start, ws.data_ptr(),
+                                                ws_bytes, st), "kv_backward")
+        if hook is not None:
+            hook(garena, lay.kv_w_start, lay.block_w_start[0])
+            hook(garena, lay.kv_b_start, lay.block_v_start[0])
+        self._last_grad_arena = garena
+        grads = []
+        for name, p in self._named_params():
+            if p.requires_grad:
+                o = lay.offsets[name]
+                grads.append(garena[o:o + p.numel()].view(p.shape))
+            else:
+                grads.append(None)
+        d_text = d.view(B, L, D) if text_needs_grad else None
+        return d_text, grads
+
+    # -- public API ----------------------------------------------------------------------------------
+    def forward(self, vision_features: torch.Tensor, text_embeddings: torch.Tensor, debug: bool = False,
+                kv_cache=None) -> torch.Tensor:
+        """Same contract as the reference `BridgeLite.forward` (bridge_module.py:406-456).
+
+        `kv_cache` (a `VisionKVCache`) is an additive, inference-only argument: when given, the
+        per-image K/V projections are read from the cache instead of being recomputed.
+        """
+        params = [p for _, p in self._named_params()]
+        needs_grad = torch.is_grad_enabled() and (text_embeddings.requires_grad or any(p.requires_grad for p in params))
+        if debug:
+            return self._forward_debug(vision_features, text_embeddings, kv_cache)
+        if needs_grad:
+            if kv_cache is not None:
+                raise RuntimeError("kv_cache is inference-only (use torch.no_grad())")
+            out = _BridgeFunction.apply(self, vision_features, text_embeddings, *params)
+        else:
+            out, _ = self._run_forward(vision_features, text_embeddings, keep_for_backward=False, kv_cache=kv_cache)
+        return out if text_embeddings.dtype == torch.float32 else out
+
+    def _forward_debug(self, vision_features, text_embeddings, kv_cache):
+        """debug=True: print the reference's per-block statistics (bridge_module.py:427-454).
+        Runs the no-grad path per block, as the reference only uses it during generation."""
+        print(f"🌉 Bridge Input - Vision: {vision_features.shape}, Text: {text_embeddings.shape}")
+        print(f"    Text stats: mean={text_embeddings.mean():.4f}, std={text_embeddings.std():.4f}")
+        print(f"    Vision stats: mean={vision_features.mean():.4f}, std={vision_features.std():.4f}")
+
+        def cb(i, before, after):
+            print(f"    Block {i + 1}: {before.mean():.4f}±{before.std():.4f} → {after.mean():.4f}±{after.std():.4f}")
+            if torch.isnan(after).any():
+                print(f"    ⚠️  NaN detected in Block {i + 1} output!")
+            if torch.isinf(after).any():
+                print(f"    ⚠️  Inf detected in Block {i + 1} output!")
+
+        params = [p for _, p in self._named_params()]
+        needs_grad = torch.is_grad_enabled() and (text_embeddings.requires_grad or any(p.requires_grad for p in params))
+        if needs_grad:
+            # keep autograd semantics; statistics are printed from a second, no-grad pass
+            with torch.no_grad():
+                was = self.training
+                self.eval()
+                self._run_forward(vision_features, text_embeddings, False, kv_cache, block_callback=cb)
+                self.train(was)
+            return _BridgeFunction.apply(self, vision_features, text_embeddings, *params)
+        out, _ = self._run_forward(vision_features, text_embeddings, False, kv_cache, block_callback=cb)
+        return out
+
+    def get_model_info(self) -> dict:
+        """Same keys as the reference (bridge_module.py:458-471)."""
+        total_params = sum(p.numel() for p in self.parameters())
+        trainable_params = sum(p.numel() for p in self.parameters() if p.requires_grad)
+        return {
+            "architecture": "Bridge-Lite",
+            "num_blocks": self.num_blocks,
+            "vision_dim": self.vision_dim,
+            "language_dim": self.language_dim,
+            "total_parameters": total_params,
+            "trainable_parameters": trainable_params,
+            "parameter_ratio": f"{trainable_params / total_params:.4f}",
+        }

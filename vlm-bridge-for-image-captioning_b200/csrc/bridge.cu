@@ -1,0 +1,331 @@
+// Whole-block forward / backward of the bridge: the host-side sequencing of the kernels in
+// gemm_sm100.cu, attention.cu and elementwise.cu for one BridgeBlock
+// (reference: BridgeBlock.forward, bridge_module.py:300-335, and its autograd backward).
+// Everything is enqueued on the caller's stream; nothing here allocates or synchronises.
+#include <string.h>
+
+#include "common.cuh"
+#include "launch.h"
+
+namespace b200b {
+
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(reinterpret_cast<uint8_t*>(b)) {}
+  template <typename T>
+  T* take(size_t count) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += al256(count * sizeof(T));
+    return p;
+  }
+};
+
+struct Dims {
+  int B, L, Nv, D, Dv, F, Hc, Hs, nb;
+  size_t T, Tv;
+  int dc, ds;  // head dims
+};
+
+static int read_dims(const b200b_bridge_dims* d, Dims* o, const char* what) {
+  if (d == nullptr) {
+    set_last_error("%s: null dims", what);
+    return B200B_ERR_ARG;
+  }
+  o->B = d->batch; o->L = d->len_text; o->Nv = d->len_vision;
+  o->D = d->dim; o->Dv = d->dim_vision; o->F = d->dim_ffn;
+  o->Hc = d->heads_cross; o->Hs = d->heads_self; o->nb = d->num_blocks;
+  if (o->B <= 0 || o->L <= 0 || o->Nv <= 0 || o->D <= 0 || o->Dv <= 0 || o->F <= 0 || o->Hc <= 0 || o->Hs <= 0 ||
+      o->nb <= 0) {
+    set_last_error("%s: all dims must be positive", what);
+    return B200B_ERR_SHAPE;
+  }
+  if ((o->D % 8) || (o->Dv % 8) || (o->F % 8) || (o->D % o->Hc) || (o->D % o->Hs)) {
+    set_last_error("%s: dim/dim_vision/dim_ffn must be multiples of 8 and dim divisible by the head counts", what);
+    return B200B_ERR_SHAPE;
+  }
+  o->T = (size_t)o->B * o->L;
+  o->Tv = (size_t)o->B * o->Nv;
+  o->dc = o->D / o->Hc;
+  o->ds = o->D / o->Hs;
+  if (o->T > 0x7fffffff || o->Tv > 0x7fffffff) {
+    set_last_error("%s: too many rows", what);
+    return B200B_ERR_SHAPE;
+  }
+  return B200B_OK;
+}
+
+// activations a block keeps for its backward
+struct Saved {
+  __nv_bfloat16 *xn1, *q, *o1, *xn2, *qkv, *o2, *xn3, *u, *h;
+  float *x1, *x2;
+  float *mean1, *rstd1, *mean2, *rstd2, *mean3, *rstd3;
+  float *lse1, *lse2;
+  size_t bytes;
+};
+
+static Saved carve_saved(const Dims& d, void* base) {
+  Carver c(base);
+  Saved s;
+  const size_t TD = d.T * d.D, TF = d.T * d.F;
+  s.xn1 = c.take<__nv_bfloat16>(TD);
+  s.q = c.take<__nv_bfloat16>(TD);
+  s.o1 = c.take<__nv_bfloat16>(TD);
+  s.xn2 = c.take<__nv_bfloat16>(TD);
+  s.qkv = c.take<__nv_bfloat16>(3 * TD);
+  s.o2 = c.take<__nv_bfloat16>(TD);
+  s.xn3 = c.take<__nv_bfloat16>(TD);
+  s.u = c.take<__nv_bfloat16>(TF);
+  s.h = c.take<__nv_bfloat16>(TF);
+  s.x1 = c.take<float>(TD);
+  s.x2 = c.take<float>(TD);
+  s.mean1 = c.take<float>(d.T); s.rstd1 = c.take<float>(d.T);
+  s.mean2 = c.take<float>(d.T); s.rstd2 = c.take<float>(d.T);
+  s.mean3 = c.take<float>(d.T); s.rstd3 = c.take<float>(d.T);
+  s.lse1 = c.take<float>((size_t)d.B * d.Hc * d.L);
+  s.lse2 = c.take<float>((size_t)d.B * d.Hs * d.L);
+  s.bytes = c.off;
+  return s;
+}
+
+// transient buffers of the backward pass
+struct BwdWs {
+  __nv_bfloat16 *dy, *du, *dxn, *dattn, *dqkv;
+  float* dx;
+  uint8_t* attn_ws; size_t attn_ws_bytes;
+  uint8_t* colsum_ws; size_t colsum_ws_bytes;
+  size_t bytes;
+};
+
+static BwdWs carve_bwd(const Dims& d, void* base) {
+  Carver c(base);
+  BwdWs w;
+  const size_t TD = d.T * d.D, TF = d.T * d.F;
+  w.dy = c.take<__nv_bfloat16>(TD);
+  w.du = c.take<__nv_bfloat16>(TF);
+  w.dxn = c.take<__nv_bfloat16>(TD);
+  w.dattn = c.take<__nv_bfloat16>(TD);
+  w.dqkv = c.take<__nv_bfloat16>(3 * TD);
+  w.dx = c.take<float>(TD);
+  const size_t a1 = b200b_attention_bwd_workspace_bytes(d.B, d.Hc, d.L, d.Nv);
+  const size_t a2 = b200b_attention_bwd_workspace_bytes(d.B, d.Hs, d.L, d.L);
+  w.attn_ws_bytes = a1 > a2 ? a1 : a2;
+  w.attn_ws = c.take<uint8_t>(w.attn_ws_bytes);
+  int maxc = d.F;
+  if (3 * d.D > maxc) maxc = 3 * d.D;
+  if (2 * d.D * d.nb > maxc) maxc = 2 * d.D * d.nb;
+  w.colsum_ws_bytes = b200b_colsum_workspace_bytes(0, maxc);
+  w.colsum_ws = c.take<uint8_t>(w.colsum_ws_bytes);
+  w.bytes = c.off;
+  return w;
+}
+
+#define B200B_TRY(expr)        \
+  do {                         \
+    int rc_ = (expr);          \
+    if (rc_ != B200B_OK) return rc_; \
+  } while (0)
+
+static int gemm(const void* a, int a_major, long long lda, const void* b, int b_major, long long ldb, int m, int n,
+                int k, int epi, void* out, long long ldo, const float* bias, const float* resid, void* aux,
+                long long ldaux, float p, uint64_t seed, uint32_t dstream, cudaStream_t st) {
+  b200b_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.a = a; g.b = b; g.a_major = a_major; g.b_major = b_major;
+  g.m = m; g.n = n; g.k = k; g.lda = lda; g.ldb = ldb;
+  g.epilogue = epi; g.block_n = 0;
+  g.out = out; g.ldo = ldo; g.aux = aux; g.ldaux = ldaux;
+  g.bias = bias; g.resid = resid; g.ldr = ldo;
+  g.beta = 0.f; g.dropout_p = p; g.seed = seed; g.dropout_stream = dstream;
+  return b200b_gemm(&g, st);
+}
+
+static int attn(bool bwd, const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                void* o, long long ldo, float* lse, const void* d_o, void* dq, long long lddq, void* dk, long long lddk,
+                void* dv, long long lddv, void* ws, size_t ws_bytes, int B, int H, int Lq, int Lk, int hd, float p,
+                uint64_t seed, uint32_t dstream, cudaStream_t st) {
+  b200b_attn_args a;
+  memset(&a, 0, sizeof(a));
+  a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv; a.o = o; a.ldo = ldo; a.lse = lse;
+  a.d_o = d_o; a.lddo = ldo; a.dq = dq; a.lddq = lddq; a.dk = dk; a.lddk = lddk; a.dv = dv; a.lddv = lddv;
+  a.workspace = ws; a.workspace_bytes = ws_bytes;
+  a.batch = B; a.heads = H; a.len_q = Lq; a.len_k = Lk; a.head_dim = hd;
+  a.dropout_p = p; a.seed = seed; a.dropout_stream = dstream;
+  return bwd ? b200b_attention_bwd(&a, st) : b200b_attention_fwd(&a, st);
+}
+
+// dropout stream ids of block i
+static inline uint32_t ds_cross(int i) { return 16u * i + 0; }
+static inline uint32_t ds_self(int i) { return 16u * i + 1; }
+static inline uint32_t ds_ffn_h(int i) { return 16u * i + 2; }
+static inline uint32_t ds_ffn_o(int i) { return 16u * i + 3; }
+
+}  // namespace b200b
+
+using namespace b200b;
+
+extern "C" size_t b200b_bridge_block_saved_bytes(const b200b_bridge_dims* dims) {
+  Dims d;
+  if (read_dims(dims, &d, "block_saved_bytes") != B200B_OK) return 0;
+  return carve_saved(d, nullptr).bytes;
+}
+
+extern "C" size_t b200b_bridge_backward_workspace_bytes(const b200b_bridge_dims* dims) {
+  Dims d;
+  if (read_dims(dims, &d, "backward_workspace_bytes") != B200B_OK) return 0;
+  return carve_bwd(d, nullptr).bytes;
+}
+
+extern "C" int b200b_bridge_kv_project(const b200b_bridge_dims* dims, const float* vision_f32, const void* wkv_all,
+                                       const float* bkv_all, void* vision_bf16, void* kv, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  Dims d;
+  B200B_TRY(read_dims(dims, &d, "kv_project"));
+  if (!vision_f32 || !wkv_all || !bkv_all || !vision_bf16 || !kv) {
+    set_last_error("kv_project: null argument");
+    return B200B_ERR_ARG;
+  }
+  const int n = 2 * d.D * d.nb;
+  B200B_TRY(b200b_cast_bf16(vision_f32, vision_bf16, (int64_t)d.Tv * d.Dv, 0.f, 0, 0, st));
+  return gemm(vision_bf16, 0, d.Dv, wkv_all, 0, d.Dv, (int)d.Tv, n, d.Dv, B200B_EPI_BF16_BIAS, kv, n, bkv_all, nullptr,
+              nullptr, 0, 0.f, 0, 0, st);
+}
+
+extern "C" int b200b_bridge_block_forward(const b200b_bridge_dims* dims, int i, const b200b_block_weights* w,
+                                          const float* x_in, const void* kv, float* x_out, void* saved,
+                                          size_t saved_bytes, float p, uint64_t seed, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  Dims d;
+  B200B_TRY(read_dims(dims, &d, "block_forward"));
+  if (!w || !x_in || !kv || !x_out || !saved || i < 0 || i >= d.nb) {
+    set_last_error("block_forward: null argument or bad block index");
+    return B200B_ERR_ARG;
+  }
+  Saved s = carve_saved(d, saved);
+  if (saved_bytes < s.bytes) {
+    set_last_error("block_forward: saved arena too small (%zu < %zu)", saved_bytes, s.bytes);
+    return B200B_ERR_WORKSPACE;
+  }
+  const int T = (int)d.T, D = d.D, F = d.F;
+  const long long ldkv = 2LL * D * d.nb;
+  const __nv_bfloat16* kblk = reinterpret_cast<const __nv_bfloat16*>(kv) + (size_t)2 * D * i;
+  const float eps = 1e-5f;
+
+  // 1. cross-attention: x1 = x + W_o * SDPA(W_q * LN(x), K_i, V_i)          (bridge_module.py:316-323)
+  B200B_TRY(b200b_layernorm_fwd(x_in, w->ln_c_g, w->ln_c_b, s.xn1, s.mean1, s.rstd1, T, D, eps, st));
+  B200B_TRY(gemm(s.xn1, 0, D, w->wq_c, 0, D, T, D, D, B200B_EPI_BF16_BIAS, s.q, D, w->bq_c, nullptr, nullptr, 0, 0.f, 0,
+                 0, st));
+  B200B_TRY(attn(false, s.q, D, kblk, ldkv, kblk + D, ldkv, s.o1, D, s.lse1, nullptr, nullptr, 0, nullptr, 0, nullptr, 0,
+                 nullptr, 0, d.B, d.Hc, d.L, d.Nv, d.dc, p, seed, ds_cross(i), st));
+  B200B_TRY(gemm(s.o1, 0, D, w->wo_c, 0, D, T, D, D, B200B_EPI_F32_BIAS_RESID, s.x1, D, w->bo_c, x_in, nullptr, 0, 0.f,
+                 0, 0, st));
+  // 2. self-attention (non-causal, unmasked)                                 (:326-328)
+  B200B_TRY(b200b_layernorm_fwd(s.x1, w->ln_s_g, w->ln_s_b, s.xn2, s.mean2, s.rstd2, T, D, eps, st));
+  B200B_TRY(gemm(s.xn2, 0, D, w->wqkv_s, 0, D, T, 3 * D, D, B200B_EPI_BF16_BIAS, s.qkv, 3 * D, w->bqkv_s, nullptr,
+                 nullptr, 0, 0.f, 0, 0, st));
+  B200B_TRY(attn(false, s.qkv, 3 * D, s.qkv + D, 3 * D, s.qkv + 2 * D, 3 * D, s.o2, D, s.lse2, nullptr, nullptr, 0,
+                 nullptr, 0, nullptr, 0, nullptr, 0, d.B, d.Hs, d.L, d.L, d.ds, p, seed, ds_self(i), st));
+  B200B_TRY(gemm(s.o2, 0, D, w->wo_s, 0, D, T, D, D, B200B_EPI_F32_BIAS_RESID, s.x2, D, w->bo_s, s.x1, nullptr, 0, 0.f,
+                 0, 0, st));
+  // 3. FFN: x3 = x2 + drop(W_2 * drop(gelu(W_1 * LN(x2))))                    (:331-333)
+  B200B_TRY(b200b_layernorm_fwd(s.x2, w->ln_f_g, w->ln_f_b, s.xn3, s.mean3, s.rstd3, T, D, eps, st));
+  B200B_TRY(gemm(s.xn3, 0, D, w->w1, 0, D, T, F, D, B200B_EPI_BF16_BIAS_GELU, s.h, F, w->b1, nullptr, s.u, F, p, seed,
+                 ds_ffn_h(i), st));
+  B200B_TRY(gemm(s.h, 0, F, w->w2, 0, F, T, D, F, B200B_EPI_F32_BIAS_RESID, x_out, D, w->b2, s.x2, nullptr, 0, p, seed,
+                 ds_ffn_o(i), st));
+  return B200B_OK;
+}
+
+extern "C" int b200b_bridge_block_backward(const b200b_bridge_dims* dims, int i, const b200b_block_weights* w,
+                                           const float* x_in, const void* kv, const void* saved, const float* d_out,
+                                           float* d_in, void* dkv, const b200b_block_grads* g, void* workspace,
+                                           size_t workspace_bytes, float p, uint64_t seed, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  Dims d;
+  B200B_TRY(read_dims(dims, &d, "block_backward"));
+  if (!w || !x_in || !kv || !saved || !d_out || !dkv || !g || !workspace || i < 0 || i >= d.nb) {
+    set_last_error("block_backward: null argument or bad block index");
+    return B200B_ERR_ARG;
+  }
+  Saved s = carve_saved(d, const_cast<void*>(saved));
+  BwdWs ws = carve_bwd(d, workspace);
+  if (workspace_bytes < ws.bytes) {
+    set_last_error("block_backward: workspace too small (%zu < %zu)", workspace_bytes, ws.bytes);
+    return B200B_ERR_WORKSPACE;
+  }
+  const int T = (int)d.T, D = d.D, F = d.F;
+  const long long ldkv = 2LL * D * d.nb;
+  const __nv_bfloat16* kblk = reinterpret_cast<const __nv_bfloat16*>(kv) + (size_t)2 * D * i;
+  __nv_bfloat16* dkblk = reinterpret_cast<__nv_bfloat16*>(dkv) + (size_t)2 * D * i;
+  const int EB = B200B_EPI_BF16_BIAS, EF = B200B_EPI_F32;
+
+  // ---- FFN ----
+  B200B_TRY(b200b_cast_bf16(d_out, ws.dy, (int64_t)T * D, p, seed, ds_ffn_o(i), st));  // d(ffn.3 out), dropout bwd
+  B200B_TRY(b200b_colsum(ws.dy, D, nullptr, nullptr, nullptr, g->b2, nullptr, T, D, ws.colsum_ws, ws.colsum_ws_bytes, st));
+  B200B_TRY(gemm(ws.dy, 1, D, s.h, 1, F, D, F, T, EF, g->w2, F, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  B200B_TRY(gemm(ws.dy, 0, D, w->w2, 1, F, T, F, D, B200B_EPI_BF16_DGELU, ws.du, F, nullptr, nullptr, s.u, F, p, seed,
+                 ds_ffn_h(i), st));
+  B200B_TRY(b200b_colsum(ws.du, F, nullptr, nullptr, nullptr, g->b1, nullptr, T, F, ws.colsum_ws, ws.colsum_ws_bytes, st));
+  B200B_TRY(gemm(ws.du, 1, F, s.xn3, 1, D, F, D, T, EF, g->w1, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  B200B_TRY(gemm(ws.du, 0, F, w->w1, 1, D, T, D, F, EB, ws.dxn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  B200B_TRY(b200b_layernorm_bwd(ws.dxn, s.x2, s.mean3, s.rstd3, w->ln_f_g, d_out, ws.dx, T, D, st));
+  B200B_TRY(b200b_colsum(ws.dxn, D, s.x2, s.mean3, s.rstd3, g->ln_f_b, g->ln_f_g, T, D, ws.colsum_ws, ws.colsum_ws_bytes,
+                         st));
+  // ---- self-attention ----
+  B200B_TRY(b200b_cast_bf16(ws.dx, ws.dy, (int64_t)T * D, 0.f, 0, 0, st));
+  B200B_TRY(b200b_colsum(ws.dy, D, nullptr, nullptr, nullptr, g->bo_s, nullptr, T, D, ws.colsum_ws, ws.colsum_ws_bytes, st));
+  B200B_TRY(gemm(ws.dy, 1, D, s.o2, 1, D, D, D, T, EF, g->wo_s, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  B200B_TRY(gemm(ws.dy, 0, D, w->wo_s, 1, D, T, D, D, EB, ws.dattn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  B200B_TRY(attn(true, s.qkv, 3 * D, s.qkv + D, 3 * D, s.qkv + 2 * D, 3 * D, s.o2, D, s.lse2, ws.dattn, ws.dqkv, 3 * D,
+                 ws.dqkv + D, 3 * D, ws.dqkv + 2 * D, 3 * D, ws.attn_ws, ws.attn_ws_bytes, d.B, d.Hs, d.L, d.L, d.ds, p,
+                 seed, ds_self(i), st));
+  B200B_TRY(b200b_colsum(ws.dqkv, 3 * D, nullptr, nullptr, nullptr, g->bqkv_s, nullptr, T, 3 * D, ws.colsum_ws,
+                         ws.colsum_ws_bytes, st));
+  B200B_TRY(gemm(ws.dqkv, 1, 3 * D, s.xn2, 1, D, 3 * D, D, T, EF, g->wqkv_s, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0,
+                 st));
+  B200B_TRY(gemm(ws.dqkv, 0, 3 * D, w->wqkv_s, 1, D, T, D, 3 * D, EB, ws.dxn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0,
+                 st));
+  B200B_TRY(b200b_layernorm_bwd(ws.dxn, s.x1, s.mean2, s.rstd2, w->ln_s_g, ws.dx, ws.dx, T, D, st));
+  B200B_TRY(b200b_colsum(ws.dxn, D, s.x1, s.mean2, s.rstd2, g->ln_s_b, g->ln_s_g, T, D, ws.colsum_ws, ws.colsum_ws_bytes,
+                         st));
+  // ---- cross-attention ----
+  B200B_TRY(b200b_cast_bf16(ws.dx, ws.dy, (int64_t)T * D, 0.f, 0, 0, st));
+  B200B_TRY(b200b_colsum(ws.dy, D, nullptr, nullptr, nullptr, g->bo_c, nullptr, T, D, ws.colsum_ws, ws.colsum_ws_bytes, st));
+  B200B_TRY(gemm(ws.dy, 1, D, s.o1, 1, D, D, D, T, EF, g->wo_c, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  B200B_TRY(gemm(ws.dy, 0, D, w->wo_c, 1, D, T, D, D, EB, ws.dattn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  __nv_bfloat16* dq = ws.dqkv;  // [T, D]
+  B200B_TRY(attn(true, s.q, D, kblk, ldkv, kblk + D, ldkv, s.o1, D, s.lse1, ws.dattn, dq, D, dkblk, ldkv, dkblk + D, ldkv,
+                 ws.attn_ws, ws.attn_ws_bytes, d.B, d.Hc, d.L, d.Nv, d.dc, p, seed, ds_cross(i), st));
+  B200B_TRY(b200b_colsum(dq, D, nullptr, nullptr, nullptr, g->bq_c, nullptr, T, D, ws.colsum_ws, ws.colsum_ws_bytes, st));
+  B200B_TRY(gemm(dq, 1, D, s.xn1, 1, D, D, D, T, EF, g->wq_c, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  B200B_TRY(gemm(dq, 0, D, w->wq_c, 1, D, T, D, D, EB, ws.dxn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  if (d_in != nullptr)
+    B200B_TRY(b200b_layernorm_bwd(ws.dxn, x_in, s.mean1, s.rstd1, w->ln_c_g, ws.dx, d_in, T, D, st));
+  B200B_TRY(b200b_colsum(ws.dxn, D, x_in, s.mean1, s.rstd1, g->ln_c_b, g->ln_c_g, T, D, ws.colsum_ws, ws.colsum_ws_bytes,
+                         st));
+  return B200B_OK;
+}
+
+extern "C" int b200b_bridge_kv_backward(const b200b_bridge_dims* dims, const void* vision_bf16, const void* dkv,
+                                        float* dwkv_all, float* dbkv_all, void* workspace, size_t workspace_bytes,
+                                        void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  Dims d;
+  B200B_TRY(read_dims(dims, &d, "kv_backward"));
+  if (!vision_bf16 || !dkv || !dwkv_all || !dbkv_all || !workspace) {
+    set_last_error("kv_backward: null argument");
+    return B200B_ERR_ARG;
+  }
+  BwdWs ws = carve_bwd(d, workspace);
+  if (workspace_bytes < ws.bytes) {
+    set_last_error("kv_backward: workspace too small (%zu < %zu)", workspace_bytes, ws.bytes);
+    return B200B_ERR_WORKSPACE;
+  }
+  const int n = 2 * d.D * d.nb;
+  B200B_TRY(b200b_colsum(dkv, n, nullptr, nullptr, nullptr, dbkv_all, nullptr, (int)d.Tv, n, ws.colsum_ws,
+                         ws.colsum_ws_bytes, st));
+  return gemm(dkv, 1, n, vision_bf16, 1, d.Dv, n, d.Dv, (int)d.Tv, B200B_EPI_F32, dwkv_all, d.Dv, nullptr, nullptr,
+              nullptr, 0, 0.f, 0, 0, st);
+}

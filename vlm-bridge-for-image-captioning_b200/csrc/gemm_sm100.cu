@@ -417,12 +417,10 @@ extern "C" int b200b_gemm(const b200b_gemm_args* a, void* stream_) {
     set_last_error("gemm: null argument");
     return B200B_ERR_ARG;
   }
-  if (a->m <= 0 || a->n <= 0 || a->k <= 0 || (a->n % 8) != 0 || (a->k % 8) != 0) {
-    set_last_error("gemm: need m,n,k > 0 and n,k multiples of 8 (got m=%d n=%d k=%d)", a->m, a->n, a->k);
-    return B200B_ERR_SHAPE;
-  }
-  if ((a->a_major && (a->m % 8) != 0)) {
-    set_last_error("gemm: MN-major A needs m %% 8 == 0 (got %d)", a->m);
+  // m and k may be ragged (TMA zero-fills out-of-bounds box elements; the epilogue masks rows);
+  // n must be a multiple of 8 because the epilogue stores 8 columns at a time.
+  if (a->m <= 0 || a->n <= 0 || a->k <= 0 || (a->n % 8) != 0) {
+    set_last_error("gemm: need m,n,k > 0 and n a multiple of 8 (got m=%d n=%d k=%d)", a->m, a->n, a->k);
     return B200B_ERR_SHAPE;
   }
   const int epi = a->epilogue;
