@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""Benchmark of the bridge hot path (BASELINE.json metric: bridge fwd+bwd samples/s; caption decode
+tokens/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one forward + backward of the bridge over one synthetic batch of config C2
+(B=8 per GPU, L=128 text tokens, Nv=257 vision tokens, vision 1024 -> language 2304, 2 blocks,
+heads 8/18, train mode with dropout 0.1 as `FullModel` builds it, full_model.py:38,72), upstream
+gradient of loss = mean(y^2), bf16 weight copies refreshed every step as after an
+optimizer update. Prints ONE JSON line (rank 0). See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# config C2 (BASELINE.json configs[1])
+B_PER_GPU, L_TEXT, N_VIS, D_VIS, D_LANG, N_BLOCKS, H_CROSS, H_SELF = 8, 128, 257, 1024, 2304, 2, 8, 18
+DROPOUT = 0.1
+# config C4 (decode): batch 32, 64 new tokens
+DEC_B, DEC_STEPS = 32, 64
+
+
+def gemm_flops_per_step(B: int, L: int, Nv: int) -> float:
+    """Algorithmic FLOPs of the dense contractions (the tcgen05 GEMM kernel) in one fwd+bwd step:
+    text-side linears forward + dgrad + wgrad, vision K/V projections forward + wgrad."""
+    T, Tv, D, Dv, F = B * L, B * Nv, D_LANG, D_VIS, 4 * D_LANG
+    text = N_BLOCKS * (2.0 * T * D * D * 6 + 4.0 * T * D * F)
+    kv = N_BLOCKS * 4.0 * Tv * Dv * D
+    return 3.0 * text + 2.0 * kv
+
+
+def total_flops_per_step(B: int, L: int, Nv: int) -> float:
+    T, D = B * L, D_LANG
+    attn_fwd = N_BLOCKS * (4.0 * B * L * Nv * D + 4.0 * B * L * L * D)
+    return gemm_flops_per_step(B, L, Nv) + 3.0 * attn_fwd
+
+
+def decode_bytes_per_step(B: int, s: int, Nv: int) -> float:
+    """Algorithmic HBM bytes of the decode cross-attention at prefix length s (bf16 cache):
+    K and V of every block read once, Q read and O written."""
+    D = D_LANG
+    return N_BLOCKS * (B * 2.0 * Nv * D * 2 + 2.0 * B * s * D * 2)
+
+
+def load_peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"bf16_burst": d.get("bf16_tflops", 1590.0), "bf16_sustained": d.get("bf16_tflops_sustained", 1400.0),
+                "hbm": d.get("hbm_gbs", 6650.0), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while a region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+        self.t0 = self.t1 = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu=timestamp,{self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def mark(self, begin: bool):
+        if begin:
+            self.t0 = time.time()
+        else:
+            self.t1 = time.time()
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        try:
+            with open(self.path) as f:
+                for line in f:
+                    parts = [x.strip() for x in line.split(",")]
+                    if len(parts) < 8:
+                        continue
+                    try:
+                        sm.append(float(parts[1]))
+                        mx.append(float(parts[2]))
+                        power.append(float(parts[3]))
+                    except ValueError:
+                        continue
+                    for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                         parts[4:8]):
+                        if val.lower() == "active":
+                            reasons.add(name)
+            os.unlink(self.path)
+        except Exception:  # noqa: BLE001
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load": samples whose power draw is in the upper half of the observed range
+        lo, hi = min(power), max(power)
+        loaded = [s for s, p in zip(sm, power) if p >= lo + 0.5 * (hi - lo)] or sm
+        return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": hi}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference bridge on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_bridge_samples_per_s(steps: int, warmup: int, budget_s: float):
+    """Times oracle fwd+bwd (the CPU restatement of the reference module) at config C2's shape.
+    If a full batch-8 step would blow the time budget, a smaller batch is used as the sample and
+    samples/s is computed from it (samples are independent in the bridge)."""
+    import torch
+
+    from oracle import bridge_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.init_state_dict(0)
+    g = torch.Generator().manual_seed(1234)
+
+    def make(b):
+        return torch.randn(b, N_VIS, D_VIS, generator=g), torch.randn(b, L_TEXT, D_LANG, generator=g)
+
+    def step(v, t):
+        O.bridge_loss_and_grads(sd, v, t, num_blocks=N_BLOCKS, heads_cross=H_CROSS, heads_self=H_SELF)
+
+    b = B_PER_GPU
+    v, t = make(b)
+    t0 = time.perf_counter()
+    step(v, t)  # first call also pays allocator warm-up
+    first = time.perf_counter() - t0
+    total = steps + warmup
+    if first * total > budget_s and b > 1:
+        b = max(1, int(b * budget_s / (first * total)))
+        v, t = make(b)
+    for _ in range(max(0, warmup - 1)):
+        step(v, t)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step(v, t)
+        times.append(time.perf_counter() - t0)
+    per_step = sum(times) / len(times)
+    sample = (f"oracle port of BridgeLite fwd+bwd (fp32, eval/no dropout), batch {b} x L{L_TEXT} x Nv{N_VIS}, "
+              f"{steps} timed steps after {warmup} warm-up, torch CPU {torch.__version__}, {cores} threads")
+    return b / per_step, per_step * 1e3, cores, sample
+
+
+def run_reference_arm(args) -> int:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    value, ms, cores, sample = cpu_bridge_samples_per_s(args.steps, args.warmup, budget_s=200.0)
+    line = {
+        "impl": "reference", "metric": "bridge fwd+bwd samples/sec", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {
+        "workload": (f"C2 bridge fwd+bwd: batch {B_PER_GPU}/GPU, text L={L_TEXT} x {D_LANG}, vision Nv={N_VIS} x {D_VIS}, "
+                     f"{N_BLOCKS} blocks, heads {H_CROSS}/{H_SELF}, train mode dropout {DROPOUT}, loss=mean(y^2); "
+                     "frozen DINOv2/Gemma are outside the hot path and not run"),
+        "global_batch": B_PER_GPU * n_gpus,
+        "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single",
+        "l2": "working set (0.95 GB fp32+bf16 weights, 0.63 GB grads, 0.25 GB activations) exceeds the 126 MB L2; no flush needed",
+        "weights": "random init (reference Xavier scheme, seed 0); bf16 copies re-cast every step",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200_arm(args) -> int:
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from vlm_bridge_b200 import BridgeLite, VisionKVCache, _lib
+    from vlm_bridge_b200.parallel import broadcast_parameters, enable_data_parallel
+
+    torch.manual_seed(0)
+    model = BridgeLite(vision_dim=D_VIS, language_dim=D_LANG, num_blocks=N_BLOCKS, num_heads_cross=H_CROSS,
+                       num_heads_self=H_SELF, dropout=DROPOUT).to(dev).train()
+    params = list(model.parameters())
+    g = torch.Generator().manual_seed(1234 + rank)
+    vision_h = torch.randn(B_PER_GPU, N_VIS, D_VIS, generator=g).pin_memory()
+    text_h = torch.randn(B_PER_GPU, L_TEXT, D_LANG, generator=g).pin_memory()
+    vision_d, text_d = vision_h.to(dev), text_h.to(dev)
+    torch.manual_seed(100 + rank)  # dropout seeds differ per rank
+    if world > 1:
+        with torch.no_grad():
+            model(vision_d, text_d)  # flattens parameters
+        broadcast_parameters(model)
+        enable_data_parallel(model)
+
+    def step(v, t):
+        model._w16_key = None            # weights count as updated by the optimizer since last step
+        for p in params:
+            p.grad = None
+        y = model(v, t)
+        loss = y.float().square().mean()
+        loss.backward()
+        return loss
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(3, args.warmup)):
+        step(vision_d, text_d)
+    # ---- timed region: device-resident inputs -------------------------------------------------
+    sync_all()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark(True)
+    e0.record()
+    for _ in range(args.steps):
+        step(vision_d, text_d)
+    e1.record()
+    sync_all()
+    sampler.mark(False)
+    launches = _lib.launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    # ---- end-to-end: host buffers in, loss out, through the public nn.Module API ---------------
+    def e2e_step():
+        v = vision_h.to(dev, non_blocking=True)
+        t = text_h.to(dev, non_blocking=True)
+        return float(step(v, t).item())
+
+    for _ in range(3):
+        e2e_step()
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e3.record()
+    sync_all()
+    ms_e2e_total = e2.elapsed_time(e3)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([ms_total, ms_e2e_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e_total = float(tt[0]), float(tt[1])
+    ms_step = ms_total / args.steps
+    ms_e2e = ms_e2e_total / args.steps
+    value = B_PER_GPU * world / (ms_step * 1e-3)
+    e2e_value = B_PER_GPU * world / (ms_e2e * 1e-3)
+
+    line = {
+        "metric": "bridge fwd+bwd samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(world),
+        "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": vision_h.numel() * 4 + text_h.numel() * 4, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+
+    if rank == 0:
+        peaks = load_peaks()
+        # ---- per-kernel timing pass (CUDA events on the launching stream, outside the timed region) ----
+        prof_steps = min(args.steps, 10)
+        torch.cuda.synchronize()
+        _lib.profile_begin(torch.cuda.current_stream().cuda_stream)
+        for _ in range(prof_steps):
+            step(vision_d, text_d)
+        entries = _lib.profile_end()
+        by_kernel: dict[str, list[float]] = {}
+        for name, ms in entries:
+            by_kernel.setdefault(name, []).append(ms)
+        gemm_ms = sum(by_kernel.get("gemm_tcgen05_kernel", [])) / prof_steps
+        all_ms = sum(ms for _, ms in entries) / prof_steps
+        gflops = gemm_flops_per_step(B_PER_GPU, L_TEXT, N_VIS)
+        achieved = gflops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        line["roofline"] = {
+            "bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peaks["bf16_sustained"],
+            "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"], "frac_of_burst_peak": achieved / peaks["bf16_burst"],
+            "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)", "traffic": None,
+            "launches_per_step": len(by_kernel.get("gemm_tcgen05_kernel", [])) / prof_steps,
+            "avg_launch_ms": gemm_ms / max(1.0, len(by_kernel.get("gemm_tcgen05_kernel", [])) / prof_steps),
+            "algorithmic_gflop_per_step": gflops / 1e9, "kernel_share_of_step": gemm_ms / all_ms if all_ms > 0 else None,
+            "step_tflops_all_kernels": total_flops_per_step(B_PER_GPU, L_TEXT, N_VIS) / (ms_step * 1e-3) / 1e12,
+            "kernel_ms_per_step": {k: sum(v) / prof_steps for k, v in sorted(by_kernel.items())},
+        }
+        # ---- decode (config C4): cached vision K/V, bridge-only loop ------------------------------
+        try:
+            line["decode"] = bench_decode(model, dev, peaks, _lib)
+        except Exception as e:  # noqa: BLE001
+            line["decode"] = {"error": repr(e)[:300]}
+        model.train()
+        # ---- CPU baseline beside it (N=1 only) ---------------------------------------------------
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms, cores, sample = cpu_bridge_samples_per_s(steps=3, warmup=1, budget_s=25.0)
+            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample,
+                                    "ms_per_step": ms}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_decode(model, dev, peaks, _lib) -> dict:
+    """Config C4: greedy-decode-shaped loop, batch 32, 64 steps, prefix length s = 1..64, bridge only
+    (the frozen LM is outside the hot path). The per-image K/V are projected once and cached."""
+    import torch
+
+    from vlm_bridge_b200 import VisionKVCache
+
+    model.eval()
+    g = torch.Generator().manual_seed(4321)
+    vision = torch.randn(DEC_B, N_VIS, D_VIS, generator=g).to(dev)
+    text = torch.randn(DEC_B, DEC_STEPS, D_LANG, generator=g).to(dev)
+
+    def loop(cache):
+        with torch.no_grad():
+            for s in range(1, DEC_STEPS + 1):
+                model(vision, text[:, :s], kv_cache=cache)
+
+    with torch.no_grad():
+        cache = VisionKVCache(model, vision)
+    loop(cache)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        with torch.no_grad():
+            cache = VisionKVCache(model, vision)   # per-image K/V projection is part of a caption
+        loop(cache)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    # uncached loop (what the reference does: re-project K/V every step)
+    e0.record()
+    loop(None)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_uncached = e0.elapsed_time(e1)
+    # kernel-level: cross-attention launches only
+    _lib.profile_begin(torch.cuda.current_stream().cuda_stream)
+    loop(cache)
+    entries = _lib.profile_end()
+    attn = [ms_ for name, ms_ in entries if name == "attn_fwd"]
+    cross_ms = sum(attn[0::2])          # per block: cross-attention first, then self-attention
+    bytes_total = sum(decode_bytes_per_step(DEC_B, s, N_VIS) for s in range(1, DEC_STEPS + 1))
+    achieved = bytes_total / (cross_ms * 1e-3) / 1e9 if cross_ms > 0 else 0.0
+    return {
+        "metric": "caption decode tokens/sec (bridge-only loop, cached vision K/V)",
+        "value": DEC_B * DEC_STEPS / (ms * 1e-3), "unit": "tokens/s", "ms_per_caption_batch": ms,
+        "uncached_tokens_per_s": DEC_B * DEC_STEPS / (ms_uncached * 1e-3),
+        "config": f"C4: batch {DEC_B}, {DEC_STEPS} new tokens, prefix recomputed every step (non-causal bridge), Nv={N_VIS}",
+        "roofline": {"bound": "hbm", "kernel": "attn_fwd (cross-attention launches)", "achieved": achieved,
+                     "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": None,
+                     "algorithmic_bytes_total": bytes_total, "kernel_ms_total": cross_ms,
+                     "note": "the 152 MB bf16 cache is comparable to the 126 MB L2, so part of it is served from L2"},
+        "kv_cache_bytes": cache.nbytes,
+    }
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

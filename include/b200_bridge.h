@@ -45,6 +45,14 @@ const char* b200b_last_error(void);
 /* number of kernels this library has launched in the calling process (all threads) */
 uint64_t b200b_launch_count(void);
 
+/* Optional per-kernel timing with CUDA events on the launching stream (used by bench.py for the
+ * roofline numbers; never on during a timed region). begin() records a start event, every kernel
+ * launched afterwards records one more, end() synchronises and returns the count; entry i is the
+ * kernel name and the milliseconds between event i and i+1. */
+int b200b_profile_begin(void* stream);
+int b200b_profile_end(void);
+const char* b200b_profile_entry(int index, float* ms);
+
 /* ------------------------------------------------------------------------------------------- *
  * Dropout: Philox4x32-10 keyed by `seed`; each fused op below names the `stream` id it uses so
  * forward and backward regenerate identical masks. p == 0 disables.

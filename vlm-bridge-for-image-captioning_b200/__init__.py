@@ -6,3 +6,4 @@ __version__ = "0.1.0"
 
 from .bridge import (BridgeBlock, BridgeLite, MultiHeadCrossAttention,  # noqa: E402,F401
                      MultiHeadSelfAttention)
+from .kv_cache import VisionKVCache  # noqa: E402,F401

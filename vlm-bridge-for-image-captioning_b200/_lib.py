@@ -81,6 +81,12 @@ def _declare(lib) -> None:
     lib.b200b_last_error.argtypes = []
     lib.b200b_launch_count.restype = C.c_uint64
     lib.b200b_launch_count.argtypes = []
+    lib.b200b_profile_begin.restype = C.c_int
+    lib.b200b_profile_begin.argtypes = [C.c_void_p]
+    lib.b200b_profile_end.restype = C.c_int
+    lib.b200b_profile_end.argtypes = []
+    lib.b200b_profile_entry.restype = C.c_char_p
+    lib.b200b_profile_entry.argtypes = [C.c_int, C.POINTER(C.c_float)]
     lib.b200b_gemm.restype = C.c_int
     lib.b200b_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
     lib.b200b_layernorm_fwd.restype = C.c_int
@@ -128,3 +134,20 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(lib().b200b_launch_count())
+
+
+def profile_begin(stream_ptr: int) -> None:
+    check(lib().b200b_profile_begin(C.c_void_p(stream_ptr)), "profile_begin")
+
+
+def profile_end() -> list[tuple[str, float]]:
+    """[(kernel name, milliseconds)] of every launch since profile_begin()."""
+    n = lib().b200b_profile_end()
+    out = []
+    ms = C.c_float()
+    for i in range(n):
+        name = lib().b200b_profile_entry(i, C.byref(ms))
+        if name is None:
+            break
+        out.append((name.decode(), float(ms.value)))
+    return out

@@ -460,6 +460,9 @@ class BridgeLite(nn.Module):
         if hook is not None:
             hook(garena, lay.kv_w_start, lay.block_w_start[0])
             hook(garena, lay.kv_b_start, lay.block_v_start[0])
+            finish = getattr(hook, "finish", None)
+            if finish is not None:
+                finish()
         self._last_grad_arena = garena
         grads = []
         for name, p in self._named_params():

@@ -3,6 +3,9 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "../../include/b200_bridge.h"
 #include "launch.h"
@@ -19,13 +22,33 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int check_launch(const char* what) {
+// ---- optional per-kernel timing (bench.py's roofline leg; off by default) ----------------------
+struct ProfEvent {
+  cudaEvent_t ev;
+  const char* what;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfEvent> g_prof_events;
+
+int check_launch(const char* what, cudaStream_t stream) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_last_error("%s: launch failed: %s", what, cudaGetErrorString(e));
     return (int)e;
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (g_prof_on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_prof_on) {
+      ProfEvent pe;
+      pe.what = what;
+      if (cudaEventCreate(&pe.ev) == cudaSuccess) {
+        cudaEventRecord(pe.ev, stream);
+        g_prof_events.push_back(pe);
+      }
+    }
+  }
   return B200B_OK;
 }
 
@@ -57,3 +80,45 @@ int device_sm_count(int* out) {
 extern "C" int b200b_abi_version(void) { return B200B_ABI_VERSION; }
 extern "C" const char* b200b_last_error(void) { return b200b::g_err; }
 extern "C" uint64_t b200b_launch_count(void) { return b200b::g_launches.load(std::memory_order_relaxed); }
+
+// Per-kernel timing. begin(stream) records a start event; every later launch of this library
+// records one more; end() synchronises and returns the number of timed launches. Entry i is the
+// time between event i-1 and event i, i.e. kernel i plus whatever else ran on the stream between
+// the two launches. Not thread safe against concurrent begin/end; meant for bench.py.
+extern "C" int b200b_profile_begin(void* stream_) {
+  using namespace b200b;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& pe : g_prof_events) cudaEventDestroy(pe.ev);
+  g_prof_events.clear();
+  ProfEvent pe;
+  pe.what = "<begin>";
+  cudaError_t e = cudaEventCreate(&pe.ev);
+  if (e != cudaSuccess) {
+    set_last_error("profile_begin: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  cudaEventRecord(pe.ev, reinterpret_cast<cudaStream_t>(stream_));
+  g_prof_events.push_back(pe);
+  g_prof_on = true;
+  return B200B_OK;
+}
+
+extern "C" int b200b_profile_end(void) {
+  using namespace b200b;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = false;
+  if (g_prof_events.empty()) return 0;
+  cudaEventSynchronize(g_prof_events.back().ev);
+  return (int)g_prof_events.size() - 1;
+}
+
+// name and milliseconds of timed launch i in [0, b200b_profile_end()); returns NULL past the end
+extern "C" const char* b200b_profile_entry(int i, float* ms) {
+  using namespace b200b;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (i < 0 || i + 1 >= (int)g_prof_events.size()) return nullptr;
+  float t = 0.f;
+  cudaEventElapsedTime(&t, g_prof_events[i].ev, g_prof_events[i + 1].ev);
+  if (ms) *ms = t;
+  return g_prof_events[i + 1].what;
+}

@@ -540,7 +540,7 @@ static int launch_fwd(const AttnParams& p, cudaStream_t stream) {
   if (rc) return rc;
   dim3 grid((p.Lq + Cfg::kBM - 1) / Cfg::kBM, p.H, p.B);
   attn_fwd_kernel<HD><<<grid, 128, Cfg::kFwdSmem, stream>>>(p);
-  return check_launch("attn_fwd");
+  return check_launch("attn_fwd", stream);
 }
 
 template <int HD>
@@ -552,15 +552,15 @@ static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
   if (rc) return rc;
   const int delta_threads = 32 * p.H;
   attn_delta_kernel<<<p.B * p.Lq, delta_threads, 0, stream>>>(p.o, p.ldo, p.d_o, p.lddo, p.delta, p.B, p.H, p.Lq, HD);
-  rc = check_launch("attn_delta");
+  rc = check_launch("attn_delta", stream);
   if (rc) return rc;
   dim3 gq((p.Lq + Cfg::kBM - 1) / Cfg::kBM, p.H, p.B);
   attn_bwd_q_kernel<HD><<<gq, 128, Cfg::kBwdQSmem, stream>>>(p);
-  rc = check_launch("attn_bwd_q");
+  rc = check_launch("attn_bwd_q", stream);
   if (rc) return rc;
   dim3 gk((p.Lk + 31) / 32, p.H, p.B);
   attn_bwd_kv_kernel<HD><<<gk, 128, Cfg::kBwdKVSmem, stream>>>(p);
-  return check_launch("attn_bwd_kv");
+  return check_launch("attn_bwd_kv", stream);
 }
 
 static bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

@@ -220,7 +220,7 @@ static int launch_rows(K kern, int rows, cudaStream_t stream, const char* what, 
   const int warps = 8;
   const int grid = (rows + warps - 1) / warps;
   kern<<<grid, warps * 32, 0, stream>>>(args...);
-  return check_launch(what);
+  return check_launch(what, stream);
 }
 
 }  // namespace b200b
@@ -332,11 +332,11 @@ extern "C" int b200b_colsum(const void* dy_bf16, int64_t ld, const float* x, con
   dim3 grid((cols + 127) / 128, chunks);
   colsum_partial_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16), (long long)ld, x,
                                                   mean, rstd, psum, pgsum, rows, cols, rows_per_chunk);
-  rc = check_launch("colsum_partial");
+  rc = check_launch("colsum_partial", stream);
   if (rc != B200B_OK) return rc;
   colsum_final_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(psum, x ? pgsum : nullptr, out_sum, out_gsum, cols,
                                                               chunks);
-  return check_launch("colsum_final");
+  return check_launch("colsum_final", stream);
 }
 
 extern "C" int b200b_cast_bf16(const float* in, void* out_bf16, int64_t n, float dropout_p, uint64_t seed,
@@ -367,5 +367,5 @@ extern "C" int b200b_cast_bf16(const float* in, void* out_bf16, int64_t n, float
   if (blocks > cap) blocks = cap;
   cast_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out_bf16), n8,
                                                     make_dropout_cfg(dropout_p, seed), dropout_stream);
-  return check_launch("cast_bf16");
+  return check_launch("cast_bf16", stream);
 }

@@ -357,7 +357,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
     configured = true;
   }
   kern<<<grid, kGemmThreads, GemmCfg<BLOCK_N>::kSmemBytes, stream>>>(ta, tb, p);
-  return check_launch("gemm_tcgen05_kernel");
+  return check_launch("gemm_tcgen05_kernel", stream);
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>

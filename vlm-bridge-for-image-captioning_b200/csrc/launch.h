@@ -9,8 +9,10 @@ namespace b200b {
 
 // records the message returned by b200b_last_error() (thread-local)
 void set_last_error(const char* fmt, ...);
-// cudaGetLastError() after a launch; bumps the process-wide launch counter on success
-int check_launch(const char* what);
+// cudaGetLastError() after a launch; bumps the process-wide launch counter on success. While a
+// profile is open (b200b_profile_begin) it also records a CUDA event on `stream`, so that the time
+// between consecutive events is attributed to the kernel named `what`.
+int check_launch(const char* what, cudaStream_t stream);
 // SM count of the current device (cached per device); fails on non-sm_100 devices
 int device_sm_count(int* out);
 
