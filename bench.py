@@ -338,10 +338,11 @@ def run_b200_arm(args) -> int:
             "kernel_ms_per_step": {k: sum(v) / prof_steps for k, v in sorted(by_kernel.items())},
         }
         # ---- decode (config C4): cached vision K/V, bridge-only loop ------------------------------
-        try:
-            line["decode"] = bench_decode(model, dev, peaks, _lib)
-        except Exception as e:  # noqa: BLE001
-            line["decode"] = {"error": repr(e)[:300]}
+        if not args.no_decode:
+            try:
+                line["decode"] = bench_decode(model, dev, peaks, _lib)
+            except Exception as e:  # noqa: BLE001
+                line["decode"] = {"error": repr(e)[:300]}
         model.train()
         # ---- CPU baseline beside it (N=1 only) ---------------------------------------------------
         if world == 1 and not args.no_cpu_baseline:
@@ -420,6 +421,7 @@ def main() -> int:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
