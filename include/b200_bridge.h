@@ -99,7 +99,7 @@ typedef struct b200b_gemm_args {
   float dropout_p;
   uint64_t seed;
   uint32_t dropout_stream;
-  uint32_t reserved;
+  uint32_t cta_group; /* 0 = choose, 1 = one CTA per 128-row tile, 2 = CTA pair per 256-row tile */
 } b200b_gemm_args;
 
 int b200b_gemm(const b200b_gemm_args* args, void* stream);

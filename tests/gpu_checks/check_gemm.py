@@ -44,6 +44,27 @@ CASES = [
     ("mnmn_wgrad_ragged_k", 4608, 1024, 2056, 1, 1, 4, 256),   # K tail (2056 vision rows)
     ("kk_auto", 1024, 6912, 2304, 0, 0, 0, 0),
 ]
+CASES = [c + (1,) for c in CASES]
+# CTA-pair (cta_group::2) variants: 256 x block_n tiles
+CASES += [
+    ("pair_kk_small_128", 256, 128, 64, 0, 0, 0, 128, 2),
+    ("pair_kk_small_256", 256, 256, 128, 0, 0, 0, 256, 2),
+    ("pair_kk_multi_128", 768, 384, 512, 0, 0, 0, 128, 2),
+    ("pair_kk_persistent_256", 2048, 9216, 2304, 0, 0, 0, 256, 2),
+    ("pair_kk_persistent_128", 2048, 2304, 2304, 0, 0, 0, 128, 2),
+    ("pair_kk_ragged", 2056, 4608, 1024, 0, 0, 0, 256, 2),
+    ("pair_kk_ragged_small", 40, 72, 136, 0, 0, 0, 128, 2),
+    ("pair_kk_gelu_drop", 512, 512, 256, 0, 0, 1, 256, 2),
+    ("pair_kk_resid", 1024, 2304, 9216, 0, 0, 2, 128, 2),
+    ("pair_kmn_dgrad", 1024, 2304, 9216, 0, 1, 0, 128, 2),
+    ("pair_kmn_dgelu", 1024, 9216, 2304, 0, 1, 3, 256, 2),
+    ("pair_mnmn_small_128", 256, 128, 64, 1, 1, 4, 128, 2),
+    ("pair_mnmn_wgrad", 9216, 2304, 1024, 1, 1, 4, 256, 2),
+    ("pair_mnmn_wgrad_128", 2304, 2304, 1024, 1, 1, 4, 128, 2),
+    ("pair_mnmn_ragged_k", 4608, 1024, 2056, 1, 1, 4, 256, 2),
+    ("auto_ffn_up", 1024, 9216, 2304, 0, 0, 0, 0, 0),
+    ("auto_proj", 1024, 2304, 2304, 0, 0, 0, 0, 0),
+]
 
 
 def run_case(i: int) -> dict:
@@ -51,7 +72,7 @@ def run_case(i: int) -> dict:
 
     from vlm_bridge_b200 import ops
 
-    name, M, N, K, am, bm, epi, bn = CASES[i]
+    name, M, N, K, am, bm, epi, bn, cg = CASES[i]
     torch.manual_seed(100 + i)
     dev = "cuda"
     a_log = (torch.randn(M, K, device=dev) * 0.5).bfloat16()   # logical A [M,K]
@@ -64,12 +85,12 @@ def run_case(i: int) -> dict:
     seed = 1234
     res = {"case": name, "M": M, "N": N, "K": K}
     if epi == 0:
-        out = ops.gemm(a, b, a_major=am, b_major=bm, epilogue=0, bias=bias, block_n=bn)
+        out = ops.gemm(a, b, a_major=am, b_major=bm, epilogue=0, bias=bias, block_n=bn, cta_group=cg)
         ref = acc + bias
         err = (out.float() - ref).abs().max().item() / ref.abs().max().item()
         tol = 1e-2
     elif epi == 1:
-        out, u = ops.gemm(a, b, a_major=am, b_major=bm, epilogue=1, bias=bias, block_n=bn,
+        out, u = ops.gemm(a, b, a_major=am, b_major=bm, epilogue=1, bias=bias, block_n=bn, cta_group=cg,
                           dropout_p=p, seed=seed, dropout_stream=3)
         u_ref = (acc + bias).bfloat16().float()
         h_ref = torch.nn.functional.gelu(u_ref).bfloat16().float()
@@ -79,7 +100,7 @@ def run_case(i: int) -> dict:
             res["keep_frac"] = keep.float().mean().item()
             err = ((out.float() - h_ref / (1 - p)) * keep).abs().max().item() / h_ref.abs().max().item()
             # mask must be reproducible
-            out2, _ = ops.gemm(a, b, a_major=am, b_major=bm, epilogue=1, bias=bias, block_n=bn,
+            out2, _ = ops.gemm(a, b, a_major=am, b_major=bm, epilogue=1, bias=bias, block_n=bn, cta_group=cg,
                                dropout_p=p, seed=seed, dropout_stream=3)
             res["mask_repro"] = bool(torch.equal(out, out2))
         else:
@@ -88,7 +109,7 @@ def run_case(i: int) -> dict:
         tol = 1.5e-2
     elif epi == 2:
         resid = torch.randn(M, N, device=dev)
-        out = ops.gemm(a, b, a_major=am, b_major=bm, epilogue=2, bias=bias, resid=resid, block_n=bn,
+        out = ops.gemm(a, b, a_major=am, b_major=bm, epilogue=2, bias=bias, resid=resid, block_n=bn, cta_group=cg,
                        dropout_p=p, seed=seed, dropout_stream=5)
         y = (acc + bias).bfloat16().float()
         if p > 0:
@@ -101,7 +122,7 @@ def run_case(i: int) -> dict:
         tol = 1.5e-2
     elif epi == 3:
         u = torch.randn(M, N, device=dev).bfloat16()
-        out = ops.gemm(a, b, a_major=am, b_major=bm, epilogue=3, aux=u, block_n=bn)
+        out = ops.gemm(a, b, a_major=am, b_major=bm, epilogue=3, aux=u, block_n=bn, cta_group=cg)
         uf = u.float().requires_grad_()
         torch.nn.functional.gelu(uf).backward(acc.bfloat16().float())
         ref = uf.grad
@@ -111,7 +132,7 @@ def run_case(i: int) -> dict:
         beta = 0.5 if "beta" in name else 0.0
         out0 = torch.randn(M, N, device=dev)
         out = out0.clone()
-        ops.gemm(a, b, a_major=am, b_major=bm, epilogue=4, out=out, beta=beta, block_n=bn)
+        ops.gemm(a, b, a_major=am, b_major=bm, epilogue=4, out=out, beta=beta, block_n=bn, cta_group=cg)
         ref = beta * out0 + acc
         err = (out - ref).abs().max().item() / ref.abs().max().item()
         tol = 1e-4
@@ -120,7 +141,7 @@ def run_case(i: int) -> dict:
     res["ok"] = bool(err < tol) and res.get("mask_repro", True)
     if res["ok"] and M * N * K >= 1024 * 2304 * 1024 and epi in (0, 4):
         # quick throughput sample (CUDA events, 20 launches after 3 warm-ups)
-        kw = dict(a_major=am, b_major=bm, epilogue=epi, block_n=bn)
+        kw = dict(a_major=am, b_major=bm, epilogue=epi, block_n=bn, cta_group=cg)
         if epi == 0:
             kw["bias"] = bias
             o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)

@@ -45,7 +45,7 @@ class GemmArgs(C.Structure):
         ("dropout_p", C.c_float),
         ("seed", C.c_uint64),
         ("dropout_stream", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("cta_group", C.c_uint32),
     ]
 
 

@@ -18,6 +18,7 @@
 // overlaps the main loop of tile i+1.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -40,6 +41,7 @@ struct GemmKernelParams {
   float beta;
   DropoutCfg drop;
   uint32_t drop_stream;
+  int debug_mode;  // bring-up experiments only: 1 = producer skips the TMA loads, 2 = MMA thread skips the MMAs
 };
 
 constexpr int kBlockM = 128;
@@ -54,24 +56,19 @@ struct GemmCfg {
   static constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 + 4 * 32 * 33 * 4;
 };
 
-// ---- epilogue for 8 consecutive columns of one row -------------------------------------------
+// ---- epilogue for 4 consecutive columns of one row ---------------------------------------------
 template <int EPI>
-__device__ __forceinline__ void epilogue8(const GemmKernelParams& p, int row, int col,
-                                          const uint32_t* v /*8 fp32 bit patterns*/) {
-  float f[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]);
+__device__ __forceinline__ void epilogue4(const GemmKernelParams& p, int row, int col, float4 acc) {
+  float f[4] = {acc.x, acc.y, acc.z, acc.w};
 
   if constexpr (EPI == B200B_EPI_BF16_BIAS || EPI == B200B_EPI_BF16_BIAS_GELU ||
                 EPI == B200B_EPI_F32_BIAS_RESID) {
     if (p.bias != nullptr) {
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
       f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-      f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
     }
   }
 
@@ -79,73 +76,113 @@ __device__ __forceinline__ void epilogue8(const GemmKernelParams& p, int row, in
   const bool use_drop = (EPI == B200B_EPI_BF16_BIAS_GELU || EPI == B200B_EPI_F32_BIAS_RESID ||
                          EPI == B200B_EPI_BF16_DGELU) &&
                         p.drop.thr != 0;
+  const int e0 = col & 4;  // position of these 4 columns inside their 8-element dropout group
   if (use_drop) {
     const uint64_t group = ((uint64_t)row * (uint64_t)p.n + (uint64_t)col) >> 3;
     bits = dropout_bits8(p.drop, p.drop_stream, group);
   }
 
   if constexpr (EPI == B200B_EPI_BF16_BIAS) {
-    uint4 o;
+    uint2 o;
     o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
-    o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col) = o;
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col) = o;
   } else if constexpr (EPI == B200B_EPI_BF16_BIAS_GELU) {
-    float h[8];
+    float h[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4; ++i) {
       f[i] = bf16_round(f[i]);          // the reference Linear output is bf16 under autocast
       h[i] = bf16_round(gelu_erf(f[i]));
-      if (use_drop) h[i] = dropout_keep(bits, i, p.drop.thr) ? h[i] * p.drop.scale : 0.0f;
+      if (use_drop) h[i] = dropout_keep(bits, e0 + i, p.drop.thr) ? h[i] * p.drop.scale : 0.0f;
     }
-    uint4 u, o;
+    uint2 u, o;
     u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]);
-    u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
     o.x = pack_bf16(h[0], h[1]); o.y = pack_bf16(h[2], h[3]);
-    o.z = pack_bf16(h[4], h[5]); o.w = pack_bf16(h[6], h[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.aux) + (long long)row * p.ldaux + col) = u;
-    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col) = o;
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.aux) + (long long)row * p.ldaux + col) = u;
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col) = o;
   } else if constexpr (EPI == B200B_EPI_F32_BIAS_RESID) {
-    const float* rp = p.resid + (long long)row * p.ldr + col;
-    const float4 r0 = *reinterpret_cast<const float4*>(rp);
-    const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
-    const float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-    float o[8];
+    const float4 r0 = *reinterpret_cast<const float4*>(p.resid + (long long)row * p.ldr + col);
+    const float r[4] = {r0.x, r0.y, r0.z, r0.w};
+    float o[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4; ++i) {
       float y = bf16_round(f[i]);
-      if (use_drop) y = dropout_keep(bits, i, p.drop.thr) ? bf16_round(y * p.drop.scale) : 0.0f;
+      if (use_drop) y = dropout_keep(bits, e0 + i, p.drop.thr) ? bf16_round(y * p.drop.scale) : 0.0f;
       o[i] = r[i] + y;
     }
-    float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col;
-    *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<float4*>(op + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col) =
+        make_float4(o[0], o[1], o[2], o[3]);
   } else if constexpr (EPI == B200B_EPI_BF16_DGELU) {
-    const uint4 uu = *reinterpret_cast<const uint4*>(
+    const uint2 uu = *reinterpret_cast<const uint2*>(
         reinterpret_cast<const __nv_bfloat16*>(p.aux) + (long long)row * p.ldaux + col);
-    const float u[8] = {bf16_lo(uu.x), bf16_hi(uu.x), bf16_lo(uu.y), bf16_hi(uu.y),
-                        bf16_lo(uu.z), bf16_hi(uu.z), bf16_lo(uu.w), bf16_hi(uu.w)};
-    float g[8];
+    const float u[4] = {bf16_lo(uu.x), bf16_hi(uu.x), bf16_lo(uu.y), bf16_hi(uu.y)};
+    float g[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4; ++i) {
       float d = bf16_round(f[i]);
-      if (use_drop) d = dropout_keep(bits, i, p.drop.thr) ? bf16_round(d * p.drop.scale) : 0.0f;
+      if (use_drop) d = dropout_keep(bits, e0 + i, p.drop.thr) ? bf16_round(d * p.drop.scale) : 0.0f;
       g[i] = d * gelu_erf_grad(u[i]);
     }
-    uint4 o;
+    uint2 o;
     o.x = pack_bf16(g[0], g[1]); o.y = pack_bf16(g[2], g[3]);
-    o.z = pack_bf16(g[4], g[5]); o.w = pack_bf16(g[6], g[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col) = o;
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col) = o;
   } else {  // B200B_EPI_F32
     float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col;
     if (p.beta != 0.0f) {
       const float4 o0 = *reinterpret_cast<const float4*>(op);
-      const float4 o1 = *reinterpret_cast<const float4*>(op + 4);
       f[0] += p.beta * o0.x; f[1] += p.beta * o0.y; f[2] += p.beta * o0.z; f[3] += p.beta * o0.w;
-      f[4] += p.beta * o1.x; f[5] += p.beta * o1.y; f[6] += p.beta * o1.z; f[7] += p.beta * o1.w;
     }
     *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
-    *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
   }
+}
+
+// Shared pieces of the two kernels ---------------------------------------------------------------
+
+// Drain this CTA's 128 x BLOCK_N accumulator stage through the fused epilogue.
+// tcgen05.ld hands each thread one accumulator ROW (32 columns at a time); storing from that
+// layout would touch 32 different cache lines per instruction. Each warp therefore transposes its
+// 32 x 32 chunk through a private padded shared-memory tile so that 8 consecutive lanes own one
+// row's 32 columns (4 each): every global load/store instruction then covers 4 full 128-byte
+// (fp32) or 64-byte (bf16) row segments.
+constexpr int kEpiLd = 33;                                  // padded row, words (conflict free both ways)
+constexpr uint32_t kEpiBytesPerWarp = 32 * kEpiLd * 4;      // 4224 B
+constexpr uint32_t kEpiBytes = 4 * kEpiBytesPerWarp;
+
+template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void drain_accumulator(const GemmKernelParams& p, uint32_t t_row, int row0 /*of this warp*/,
+                                                  int n_idx, float* stage /*this warp's tile*/, int lane) {
+  const int r_sub = lane >> 3, cg = lane & 7;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    if (n_idx + c0 >= p.n) break;  // warp-uniform
+    uint32_t v[32];
+    tmem_ld_32x32(t_row + (uint32_t)c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) stage[lane * kEpiLd + j] = __uint_as_float(v[j]);
+    __syncwarp();
+    const int col = n_idx + c0 + 4 * cg;
+    if (col < p.n) {
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) {
+        const int r = 4 * pass + r_sub;
+        const float* sp = stage + r * kEpiLd + 4 * cg;
+        const float4 acc = make_float4(sp[0], sp[1], sp[2], sp[3]);
+        if (row0 + r < p.m) epilogue4<EPI>(p, row0 + r, col, acc);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// The 64-bit shared-memory descriptors differ between k steps / stages only in the 14-bit start
+// address field, so the issuing thread keeps the constant high words and adds to the low word.
+template <bool MN>
+struct DescConsts {
+  static constexpr uint32_t kLbo = MN ? 8192u : 16u;
+  static constexpr uint32_t kKStep16 = (MN ? 2048u : 32u) >> 4;  // start-address units per 16-wide k step
+};
+__device__ __forceinline__ uint64_t desc_with_lo(uint64_t base, uint32_t add16) {
+  return base + (uint64_t)add16;  // never carries out of the 14-bit field: smem addresses < 256 KiB
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
@@ -156,8 +193,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   constexpr int kStages = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
@@ -166,6 +201,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // 32-bit shared addresses, computed once
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+  const uint32_t tfull0 = smem_u32(tmem_full_bar), tempty0 = smem_u32(tmem_empty_bar);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -189,7 +229,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
 
   if (warp == 0) {
@@ -200,25 +239,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       const int m_idx = (tile % p.num_m_blocks) * kBlockM;
       const int n_idx = (tile / p.num_m_blocks) * BLOCK_N;
       for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (lane == 0) {
-          uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          const int k_idx = kb * kBlockK;
-          if constexpr (!A_MN) {
-            tma_load_2d(sa, &tm_a, &full_bar[stage], k_idx, m_idx);  // box {64 k, 128 rows}
+        mbar_wait_a(empty0 + 8u * stage, phase ^ 1);
+        if (elect_one()) {
+          const uint32_t sa = smem0 + (uint32_t)stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint32_t fb = full0 + 8u * stage;
+          if (p.debug_mode == 1) {
+            mbar_arrive_a(fb);
           } else {
+            mbar_arrive_expect_tx_a(fb, Cfg::kStageBytes);
+            const int k_idx = kb * kBlockK;
+            if constexpr (!A_MN) {
+              tma_load_2d_a(sa, &tm_a, fb, k_idx, m_idx);  // box {64 k, 128 rows}
+            } else {
 #pragma unroll
-            for (int j = 0; j < kBlockM / 64; ++j)                   // box {64 m, 64 k} per atom
-              tma_load_2d(sa + j * 8192, &tm_a, &full_bar[stage], m_idx + 64 * j, k_idx);
-          }
-          if constexpr (!B_MN) {
-            tma_load_2d(sb, &tm_b, &full_bar[stage], k_idx, n_idx);  // box {64 k, BLOCK_N rows}
-          } else {
+              for (int j = 0; j < kBlockM / 64; ++j)       // box {64 m, 64 k} per atom
+                tma_load_2d_a(sa + j * 8192, &tm_a, fb, m_idx + 64 * j, k_idx);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d_a(sb, &tm_b, fb, k_idx, n_idx);  // box {64 k, BLOCK_N rows}
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_2d(sb + j * 8192, &tm_b, &full_bar[stage], n_idx + 64 * j, k_idx);
+              for (int j = 0; j < BLOCK_N / 64; ++j)
+                tma_load_2d_a(sb + j * 8192, &tm_b, fb, n_idx + 64 * j, k_idx);
+            }
           }
         }
         __syncwarp();
@@ -231,31 +275,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     // K-major: 8-row groups 1024 B apart; advancing 16 k elements = +32 B inside the swizzle row.
     // MN-major: 64-wide MN atoms 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO);
     //           advancing 16 k rows = +2048 B.
-    constexpr uint32_t a_lbo = A_MN ? 8192u : 16u, b_lbo = B_MN ? 8192u : 16u;
-    constexpr uint32_t a_kstep = A_MN ? 2048u : 32u, b_kstep = B_MN ? 2048u : 32u;
+    const uint64_t adesc0 = umma_smem_desc(smem0, DescConsts<A_MN>::kLbo, 1024u);
+    const uint64_t bdesc0 = umma_smem_desc(smem0 + Cfg::kABytes, DescConsts<B_MN>::kLbo, 1024u);
     int stage = 0;
     uint32_t phase = 0;
     int iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
-      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      mbar_wait_a(tempty0 + 8u * acc, acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
       for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait_a(full0 + 8u * stage, phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
+        if (elect_one()) {
+          const uint32_t soff16 = ((uint32_t)stage * Cfg::kStageBytes) >> 4;
+          if (p.debug_mode != 2) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t adesc = umma_smem_desc(sa + k * a_kstep, a_lbo, 1024u);
-            const uint64_t bdesc = umma_smem_desc(sb + k * b_kstep, b_lbo, 1024u);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              umma_bf16(d_tmem, desc_with_lo(adesc0, soff16 + k * DescConsts<A_MN>::kKStep16),
+                        desc_with_lo(bdesc0, soff16 + k * DescConsts<B_MN>::kKStep16), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
-          umma_commit(&empty_bar[stage]);                       // frees the smem stage
-          if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator ready
+          umma_commit_a(empty0 + 8u * stage);                              // frees the smem stage
+          if (kb == p.num_k_blocks - 1) umma_commit_a(tfull0 + 8u * acc);  // accumulator ready
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -264,39 +308,189 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   } else {
     // ------------------------------- epilogue -----------------------------------------------
     const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are visible to this warp
+    float* epi_stage = reinterpret_cast<float*>(smem_gen + (size_t)kStages * Cfg::kStageBytes) + quad * 32 * kEpiLd;
     int iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       const int m_idx = (tile % p.num_m_blocks) * kBlockM;
       const int n_idx = (tile / p.num_m_blocks) * BLOCK_N;
-      const int row = m_idx + quad * 32 + lane;
-      const bool row_ok = row < p.m;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      mbar_wait_a(tfull0 + 8u * acc, acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        if (n_idx + c0 >= p.n) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int col = n_idx + c0 + 8 * j;
-            if (col < p.n) epilogue8<EPI>(p, row, col, &v[8 * j]);
-          }
-        }
-      }
+      drain_accumulator<BLOCK_N, EPI>(p, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N),
+                                      m_idx + quad * 32, n_idx, epi_stage, lane);
       tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
+      mbar_arrive_a(tempty0 + 8u * acc);
     }
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ================================================================================================
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BLOCK_N tile.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (BLOCK_N/2 rows) per k block; the
+// even CTA's MMA thread issues one 256 x BLOCK_N x 16 tcgen05.mma per k step that reads both CTAs'
+// shared memory, so every B element is fetched from L2 once per 256 output rows instead of once
+// per 128. Each CTA's TMEM holds its own 128 accumulator rows (all BLOCK_N columns) and is drained
+// by its own epilogue warps.
+//   full[s]        lives in the even CTA; both CTAs' TMA loads credit it (2 x stage bytes)
+//   empty[s]       one per CTA, released by a multicast tcgen05.commit
+//   tmem_full[a]   one per CTA, multicast commit after the last k block
+//   tmem_empty[a]  even CTA only, 256 arrivals (128 local + 128 remote epilogue threads)
+// ================================================================================================
+template <int BLOCK_N>
+struct GemmPairCfg {
+  static constexpr int kStages = (BLOCK_N == 256) ? 6 : 8;
+  static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;          // this CTA's 128 rows
+  static constexpr uint32_t kBBytes = (BLOCK_N / 2) * kBlockK * 2;    // this CTA's half of B
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 + kEpiBytes;
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                         const GemmKernelParams p) {
+  using Cfg = GemmPairCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kHalfN = BLOCK_N / 2;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+  __shared__ __align__(8) uint64_t empty_bar[kStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int pair_id = (int)cluster_id_x();
+  const int num_pairs = (int)cluster_nctaid_x();
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+  const uint32_t tfull0 = smem_u32(tmem_full_bar), tempty0 = smem_u32(tmem_empty_bar);
+  const uint32_t full0_even = full0 & 0xFEFFFFFFu;          // same offset in the pair's even CTA
+  const uint32_t tempty0_even = mapa_u32(tempty0, 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar[0], 1);
+    mbar_init(&tmem_full_bar[1], 1);
+    mbar_init(&tmem_empty_bar[0], 256);
+    mbar_init(&tmem_empty_bar[1], 256);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(&tmem_base_smem, Cfg::kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / TMA credit
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;  // num_m_blocks counts 256-row pair tiles
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer (both CTAs) --------------------------------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      const int m_idx = (tile % p.num_m_blocks) * (2 * kBlockM) + (int)cta_rank * kBlockM;
+      const int n_idx = (tile / p.num_m_blocks) * BLOCK_N + (int)cta_rank * kHalfN;
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        mbar_wait_a(empty0 + 8u * stage, phase ^ 1);
+        if (elect_one()) {
+          const uint32_t sa = smem0 + (uint32_t)stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint32_t fb = full0_even + 8u * stage;
+          if (leader) mbar_arrive_expect_tx_a(full0 + 8u * stage, 2 * Cfg::kStageBytes);
+          const int k_idx = kb * kBlockK;
+          if constexpr (!A_MN) {
+            tma_load_2d_pair_a(sa, &tm_a, fb, k_idx, m_idx);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kBlockM / 64; ++j) tma_load_2d_pair_a(sa + j * 8192, &tm_a, fb, m_idx + 64 * j, k_idx);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_pair_a(sb, &tm_b, fb, k_idx, n_idx);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kHalfN / 64; ++j) tma_load_2d_pair_a(sb + j * 8192, &tm_b, fb, n_idx + 64 * j, k_idx);
+          }
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer (even CTA only) ------------------------------
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBlockM, BLOCK_N, A_MN, B_MN);
+      const uint64_t adesc0 = umma_smem_desc(smem0, DescConsts<A_MN>::kLbo, 1024u);
+      const uint64_t bdesc0 = umma_smem_desc(smem0 + Cfg::kABytes, DescConsts<B_MN>::kLbo, 1024u);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        mbar_wait_a(tempty0 + 8u * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait_a(full0 + 8u * stage, phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t soff16 = ((uint32_t)stage * Cfg::kStageBytes) >> 4;
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              umma_bf16_pair(d_tmem, desc_with_lo(adesc0, soff16 + k * DescConsts<A_MN>::kKStep16),
+                             desc_with_lo(bdesc0, soff16 + k * DescConsts<B_MN>::kKStep16), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_pair_a(empty0 + 8u * stage, 0b11);
+            if (kb == p.num_k_blocks - 1) umma_commit_pair_a(tfull0 + 8u * acc, 0b11);
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------- epilogue (both CTAs, own 128 rows) ----------------------
+    const int quad = warp & 3;
+    float* epi_stage = reinterpret_cast<float*>(smem_gen + (size_t)kStages * Cfg::kStageBytes) + quad * 32 * kEpiLd;
+    int iter = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++iter) {
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      const int m_idx = (tile % p.num_m_blocks) * (2 * kBlockM) + (int)cta_rank * kBlockM;
+      const int n_idx = (tile / p.num_m_blocks) * BLOCK_N;
+      mbar_wait_a(tfull0 + 8u * acc, acc_phase);
+      tc_fence_after();
+      drain_accumulator<BLOCK_N, EPI>(p, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N),
+                                      m_idx + quad * 32, n_idx, epi_stage, lane);
+      tc_fence_before();
+      mbar_arrive_cluster_a(tempty0_even + 8u * acc);  // the even CTA's MMA thread owns the accumulator handshake
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still touch its smem / barriers
+  if (warp == 1) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -342,43 +536,58 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uin
   return B200B_OK;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+template <bool PAIR, int BLOCK_N, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, int grid,
                        cudaStream_t stream) {
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI>;
   static bool configured = false;  // benign race: attribute set is idempotent
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)GemmCfg<BLOCK_N>::kSmemBytes);
-    if (e != cudaSuccess) {
-      set_last_error("cudaFuncSetAttribute(gemm) failed: %s", cudaGetErrorString(e));
-      return (int)e;
+  if constexpr (PAIR) {
+    auto kern = gemm_tcgen05_pair_kernel<BLOCK_N, A_MN, B_MN, EPI>;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)GemmPairCfg<BLOCK_N>::kSmemBytes);
+      if (e != cudaSuccess) {
+        set_last_error("cudaFuncSetAttribute(gemm pair) failed: %s", cudaGetErrorString(e));
+        return (int)e;
+      }
+      configured = true;
     }
-    configured = true;
+    kern<<<grid, kGemmThreads, GemmPairCfg<BLOCK_N>::kSmemBytes, stream>>>(ta, tb, p);
+    return check_launch("gemm_tcgen05_pair_kernel", stream);
+  } else {
+    auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI>;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)GemmCfg<BLOCK_N>::kSmemBytes);
+      if (e != cudaSuccess) {
+        set_last_error("cudaFuncSetAttribute(gemm) failed: %s", cudaGetErrorString(e));
+        return (int)e;
+      }
+      configured = true;
+    }
+    kern<<<grid, kGemmThreads, GemmCfg<BLOCK_N>::kSmemBytes, stream>>>(ta, tb, p);
+    return check_launch("gemm_tcgen05_kernel", stream);
   }
-  kern<<<grid, kGemmThreads, GemmCfg<BLOCK_N>::kSmemBytes, stream>>>(ta, tb, p);
-  return check_launch("gemm_tcgen05_kernel", stream);
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <bool PAIR, int BLOCK_N, bool A_MN, bool B_MN>
 static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, int grid,
                         cudaStream_t stream) {
   switch (epi) {
     case B200B_EPI_BF16_BIAS:
-      return launch_gemm<BLOCK_N, A_MN, B_MN, B200B_EPI_BF16_BIAS>(ta, tb, p, grid, stream);
+      return launch_gemm<PAIR, BLOCK_N, A_MN, B_MN, B200B_EPI_BF16_BIAS>(ta, tb, p, grid, stream);
     case B200B_EPI_BF16_DGELU:
-      return launch_gemm<BLOCK_N, A_MN, B_MN, B200B_EPI_BF16_DGELU>(ta, tb, p, grid, stream);
+      return launch_gemm<PAIR, BLOCK_N, A_MN, B_MN, B200B_EPI_BF16_DGELU>(ta, tb, p, grid, stream);
     case B200B_EPI_F32:
-      return launch_gemm<BLOCK_N, A_MN, B_MN, B200B_EPI_F32>(ta, tb, p, grid, stream);
+      return launch_gemm<PAIR, BLOCK_N, A_MN, B_MN, B200B_EPI_F32>(ta, tb, p, grid, stream);
     default:
       break;
   }
   if constexpr (!A_MN && !B_MN) {
     switch (epi) {
       case B200B_EPI_BF16_BIAS_GELU:
-        return launch_gemm<BLOCK_N, false, false, B200B_EPI_BF16_BIAS_GELU>(ta, tb, p, grid, stream);
+        return launch_gemm<PAIR, BLOCK_N, false, false, B200B_EPI_BF16_BIAS_GELU>(ta, tb, p, grid, stream);
       case B200B_EPI_F32_BIAS_RESID:
-        return launch_gemm<BLOCK_N, false, false, B200B_EPI_F32_BIAS_RESID>(ta, tb, p, grid, stream);
+        return launch_gemm<PAIR, BLOCK_N, false, false, B200B_EPI_F32_BIAS_RESID>(ta, tb, p, grid, stream);
       default:
         break;
     }
@@ -387,24 +596,41 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
   return B200B_ERR_ARG;
 }
 
-template <int BLOCK_N>
+template <bool PAIR, int BLOCK_N>
 static int dispatch_major(int a_mn, int b_mn, int epi, const CUtensorMap& ta, const CUtensorMap& tb,
                           const GemmKernelParams& p, int grid, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return dispatch_epi<BLOCK_N, false, false>(epi, ta, tb, p, grid, stream);
-  if (!a_mn && b_mn) return dispatch_epi<BLOCK_N, false, true>(epi, ta, tb, p, grid, stream);
-  if (a_mn && b_mn) return dispatch_epi<BLOCK_N, true, true>(epi, ta, tb, p, grid, stream);
+  if (!a_mn && !b_mn) return dispatch_epi<PAIR, BLOCK_N, false, false>(epi, ta, tb, p, grid, stream);
+  if (!a_mn && b_mn) return dispatch_epi<PAIR, BLOCK_N, false, true>(epi, ta, tb, p, grid, stream);
+  if (a_mn && b_mn) return dispatch_epi<PAIR, BLOCK_N, true, true>(epi, ta, tb, p, grid, stream);
   set_last_error("gemm: a_major=1,b_major=0 is not built");
   return B200B_ERR_ARG;
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-int choose_block_n(int m, int n, int num_sms) {
-  const long long mb = (m + kBlockM - 1) / kBlockM;
-  const long long t256 = mb * ((n + 255) / 256), t128 = mb * ((n + 127) / 128);
-  const double c256 = (double)((t256 + num_sms - 1) / num_sms) * 256.0;
-  const double c128 = (double)((t128 + num_sms - 1) / num_sms) * 128.0 * 1.08;  // 128-wide tiles read more smem per flop
-  return c128 < c256 ? 128 : 256;
+// Tile configuration: CTAs per tile (1 or 2) and tile width. The cost model counts waves of
+// tiles over the SMs times a per-tile cost proportional to the tile's k-loop length, with a
+// penalty for configurations that fetch more operand bytes from L2 per flop (measured: the main
+// loop is paced by operand delivery, not by the tensor pipe, for 128-row tiles).
+struct TileChoice {
+  int cta_group, block_n;
+};
+
+TileChoice choose_tile(int m, int n, int num_sms) {
+  // CTA pairs beat single CTAs on every bridge shape measured (profiles/r01_gemm_tile_sweep.jsonl);
+  // the width is chosen by counting waves of pair tiles over the num_sms/2 pairs. 128-wide tiles
+  // sustain ~88% of the 256-wide main-loop rate.
+  const long long units = num_sms / 2;
+  double best = 1e300;
+  TileChoice out{2, 256};
+  const int widths[2] = {256, 128};
+  for (int bn : widths) {
+    const long long tiles = ((m + 255) / 256) * (long long)((n + bn - 1) / bn);
+    const long long waves = (tiles + units - 1) / units;
+    const double cost = (double)waves * bn / (bn == 256 ? 1.0 : 0.88);
+    if (cost < best) { best = cost; out = {2, bn}; }
+  }
+  return out;
 }
 
 }  // namespace b200b
@@ -459,23 +685,33 @@ extern "C" int b200b_gemm(const b200b_gemm_args* a, void* stream_) {
   if (rc != B200B_OK) return rc;
 
   int block_n = a->block_n;
-  if (block_n == 0) block_n = choose_block_n(a->m, a->n, num_sms);
-  if (block_n != 128 && block_n != 256) {
-    set_last_error("gemm: block_n must be 0, 128 or 256");
+  int cta_group = (int)a->cta_group;
+  if (block_n == 0 || cta_group == 0) {
+    const TileChoice c = choose_tile(a->m, a->n, num_sms);
+    if (block_n == 0 && cta_group == 0) { block_n = c.block_n; cta_group = c.cta_group; }
+    else if (block_n == 0) block_n = 256;
+    else cta_group = 1;
+  }
+  if ((block_n != 128 && block_n != 256) || (cta_group != 1 && cta_group != 2)) {
+    set_last_error("gemm: block_n must be 0, 128 or 256 and cta_group 0, 1 or 2");
     return B200B_ERR_ARG;
   }
+  const bool pair = cta_group == 2;
+  // rows of the B tile one CTA stages: the whole tile, or half of it in a CTA pair
+  const int b_rows = pair ? block_n / 2 : block_n;
 
   CUtensorMap ta, tb;
   if (!a->a_major) rc = make_tmap_bf16(&ta, a->a, (uint64_t)a->k, (uint64_t)a->m, (uint64_t)a->lda, kBlockM);
   else             rc = make_tmap_bf16(&ta, a->a, (uint64_t)a->m, (uint64_t)a->k, (uint64_t)a->lda, kBlockK);
   if (rc != B200B_OK) return rc;
-  if (!a->b_major) rc = make_tmap_bf16(&tb, a->b, (uint64_t)a->k, (uint64_t)a->n, (uint64_t)a->ldb, (uint32_t)block_n);
+  if (!a->b_major) rc = make_tmap_bf16(&tb, a->b, (uint64_t)a->k, (uint64_t)a->n, (uint64_t)a->ldb, (uint32_t)b_rows);
   else             rc = make_tmap_bf16(&tb, a->b, (uint64_t)a->n, (uint64_t)a->k, (uint64_t)a->ldb, kBlockK);
   if (rc != B200B_OK) return rc;
 
   GemmKernelParams p;
   p.m = a->m; p.n = a->n; p.k = a->k;
-  p.num_m_blocks = (a->m + kBlockM - 1) / kBlockM;
+  const int tile_m = pair ? 2 * kBlockM : kBlockM;
+  p.num_m_blocks = (a->m + tile_m - 1) / tile_m;
   p.num_n_blocks = (a->n + block_n - 1) / block_n;
   p.num_k_blocks = (a->k + kBlockK - 1) / kBlockK;
   p.out = a->out; p.ldo = a->ldo;
@@ -485,9 +721,17 @@ extern "C" int b200b_gemm(const b200b_gemm_args* a, void* stream_) {
   p.beta = a->beta;
   p.drop = make_dropout_cfg(a->dropout_p, a->seed);
   p.drop_stream = a->dropout_stream;
+  static const int debug_mode = [] { const char* e = getenv("B200B_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
+  p.debug_mode = debug_mode;
 
   const long long tiles = (long long)p.num_m_blocks * p.num_n_blocks;
+  if (pair) {
+    const long long pairs = num_sms / 2;
+    const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);
+    if (block_n == 256) return dispatch_major<true, 256>(a->a_major, a->b_major, epi, ta, tb, p, grid, stream);
+    return dispatch_major<true, 128>(a->a_major, a->b_major, epi, ta, tb, p, grid, stream);
+  }
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-  if (block_n == 256) return dispatch_major<256>(a->a_major, a->b_major, epi, ta, tb, p, grid, stream);
-  return dispatch_major<128>(a->a_major, a->b_major, epi, ta, tb, p, grid, stream);
+  if (block_n == 256) return dispatch_major<false, 256>(a->a_major, a->b_major, epi, ta, tb, p, grid, stream);
+  return dispatch_major<false, 128>(a->a_major, a->b_major, epi, ta, tb, p, grid, stream);
 }

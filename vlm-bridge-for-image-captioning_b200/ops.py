@@ -32,7 +32,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_major: int = 0, b_major: int = 0
          epilogue: int = EPI_BF16_BIAS, out: torch.Tensor | None = None,
          bias: torch.Tensor | None = None, aux: torch.Tensor | None = None,
          resid: torch.Tensor | None = None, beta: float = 0.0, dropout_p: float = 0.0,
-         seed: int = 0, dropout_stream: int = 0, block_n: int = 0) -> torch.Tensor:
+         seed: int = 0, dropout_stream: int = 0, block_n: int = 0, cta_group: int = 0) -> torch.Tensor:
     """acc[m,n] = sum_k A(m,k) B(n,k) on tcgen05 tensor cores with a fused epilogue.
 
     a_major=0: a is [M,K]; a_major=1: a is [K,M]. b_major=0: b is [N,K]; b_major=1: b is [K,N].
@@ -59,7 +59,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_major: int = 0, b_major: int = 0
         out=out.data_ptr(), ldo=out.stride(0),
         aux=_ptr(aux), ldaux=0 if aux is None else aux.stride(0),
         bias=_ptr(bias), resid=_ptr(resid), ldr=0 if resid is None else resid.stride(0),
-        beta=beta, dropout_p=dropout_p, seed=seed, dropout_stream=dropout_stream, reserved=0)
+        beta=beta, dropout_p=dropout_p, seed=seed, dropout_stream=dropout_stream, cta_group=cta_group)
     _lib.check(_lib.lib().b200b_gemm(C.byref(args), _stream_ptr()), "gemm")
     if epilogue == EPI_BF16_BIAS_GELU:
         return out, aux
