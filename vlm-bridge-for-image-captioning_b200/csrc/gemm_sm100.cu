@@ -5,17 +5,21 @@
 // Replaces every nn.Linear of the reference bridge (bridge_module.py:98-100,118,196-198,216,
 // 292,295) and the dgrad / wgrad matmuls autograd derives from them.
 //
-// Roles (192 threads, one CTA per SM):
-//   warp 0      TMA producer   : waits empty[s], arms full[s] with the stage byte count, issues
+// Roles (320 threads, one CTA per SM):
+//   warp 8      TMA producer   : waits empty[s], arms full[s] with the stage byte count, issues
 //                                the A and B tile loads
-//   warp 1      MMA issuer     : owns TMEM (alloc/dealloc); waits full[s]; lane 0 issues 4
+//   warp 9      MMA issuer     : owns TMEM (alloc/dealloc); waits full[s]; lane 0 issues 4
 //                                tcgen05.mma per 64-wide k block and commits to empty[s]; after the
 //                                last k block commits to tmem_full[acc]
-//   warps 2..5  epilogue       : wait tmem_full[acc]; each warp drains its 32-lane TMEM quadrant
-//                                with tcgen05.ld (thread = one output row, 32 columns at a time),
-//                                applies the epilogue and stores; then arrives on tmem_empty[acc]
+//   warps 0..7  epilogue       : wait tmem_full[acc]; two warps share each 32-lane TMEM quadrant
+//                                (alternating 32-column chunks); tcgen05.ld (thread = one output
+//                                row, 32 columns), transpose through shared memory, fused epilogue
+//                                with the residual / aux / bias operands of the NEXT chunk already
+//                                in flight; then arrive on tmem_empty[acc]
 // The accumulator is double buffered (2 x BLOCK_N TMEM columns) so the epilogue of tile i
-// overlaps the main loop of tile i+1.
+// overlaps the main loop of tile i+1. The two single-thread roles sit on the HIGHEST warp ids: the
+// SM sub-partition arbiter prefers higher warp ids, so the arithmetic-heavy epilogue warps that
+// share their schedulers can never delay a TMA issue or an MMA issue.
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -47,7 +51,10 @@ struct GemmKernelParams {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
+constexpr int kProducerWarp = kEpiWarps;      // warp 8
+constexpr int kMmaWarp = kEpiWarps + 1;       // warp 9
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -56,82 +63,156 @@ struct GemmCfg {
   static constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 + 4 * 32 * 33 * 4;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 + kEpiWarps * 32 * 33 * 4;
 };
 
-// ---- epilogue for 4 consecutive columns of one row ---------------------------------------------
+// ---- fused epilogue -----------------------------------------------------------------------------
+// Work unit: a GROUP = 4 passes of (4 rows x 8 lanes x 4 columns) = 16 rows x 32 columns of one
+// warp's 32 x 32 chunk. The loop over (chunk, group) is deliberately NOT unrolled: the first version
+// unrolled all 8 passes of all chunks and its ~10k SASS instructions thrashed the instruction cache
+// (ncu: stall_no_inst 41% of samples, profiles/r01_ncu_gemm_gelu_v3_*). One group body is ~0.5k
+// instructions. Global operands of the NEXT group (residual rows, saved pre-activations, bias) are
+// fetched before the arithmetic of the current one, and those of a tile's first group before the
+// accumulator is even ready, so no load latency sits between a load and the store that needs it.
+constexpr int kGroupPasses = 4;
+
 template <int EPI>
-__device__ __forceinline__ void epilogue4(const GemmKernelParams& p, int row, int col, float4 acc) {
+struct EpiOperands {
+  float4 bias;                 // BF16_BIAS, BF16_BIAS_GELU, F32_BIAS_RESID
+  float4 resid[kGroupPasses];  // F32_BIAS_RESID
+  uint2 aux[kGroupPasses];     // BF16_DGELU (the saved pre-activation u)
+};                             // members an epilogue does not use are never touched: no registers
+
+template <int EPI>
+constexpr bool kEpiHasDropout =
+    (EPI == B200B_EPI_BF16_BIAS_GELU || EPI == B200B_EPI_F32_BIAS_RESID || EPI == B200B_EPI_BF16_DGELU);
+
+// rows row0 + 4*pass + r_sub (pass < 4), columns [col, col+4)
+template <int EPI>
+__device__ __forceinline__ void epi_fetch(const GemmKernelParams& p, int row0, int col, int r_sub,
+                                          EpiOperands<EPI>& o) {
+  const bool col_ok = col < p.n;
+  if constexpr (EPI == B200B_EPI_BF16_BIAS || EPI == B200B_EPI_BF16_BIAS_GELU || EPI == B200B_EPI_F32_BIAS_RESID) {
+    o.bias = (p.bias != nullptr && col_ok) ? __ldg(reinterpret_cast<const float4*>(p.bias + col))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if constexpr (EPI == B200B_EPI_F32_BIAS_RESID) {
+#pragma unroll
+    for (int pass = 0; pass < kGroupPasses; ++pass) {
+      const int r = row0 + 4 * pass + r_sub;
+      o.resid[pass] = (col_ok && r < p.m) ? *reinterpret_cast<const float4*>(p.resid + (long long)r * p.ldr + col)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if constexpr (EPI == B200B_EPI_BF16_DGELU) {
+#pragma unroll
+    for (int pass = 0; pass < kGroupPasses; ++pass) {
+      const int r = row0 + 4 * pass + r_sub;
+      o.aux[pass] = (col_ok && r < p.m)
+                        ? *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) +
+                                                          (long long)r * p.ldaux + col)
+                        : make_uint2(0u, 0u);
+    }
+  }
+}
+
+// One copy of the 10 Philox rounds per kernel instead of one per call site.
+static __device__ __noinline__ uint4 dropout_bits8_call(uint32_t seed_lo, uint32_t seed_hi, uint32_t stream,
+                                                        uint32_t group_lo, uint32_t group_hi) {
+  return philox4x32_10(make_uint4(group_lo, group_hi, stream, 0x0b200b00u), make_uint2(seed_lo, seed_hi));
+}
+
+// Dropout decisions of one group: the two lanes that share an 8-element dropout group (lane ^ 1)
+// each run Philox for one of two consecutive passes and swap the halves they do not need.
+// Executed by all 32 lanes (shuffles); dropout disabled -> thr == 0 keeps everything.
+__device__ __forceinline__ void epi_dropout_bits(const GemmKernelParams& p, int row0, int col, int r_sub, int cg,
+                                                 uint2 (&w)[kGroupPasses]) {
+#pragma unroll
+  for (int i = 0; i < kGroupPasses; ++i) w[i] = make_uint2(0u, 0u);
+  if (p.drop.thr == 0) return;  // warp-uniform
+  const bool odd = (cg & 1) != 0;
+#pragma unroll
+  for (int pp = 0; pp < kGroupPasses; pp += 2) {
+    const int row = row0 + 4 * (pp + (odd ? 1 : 0)) + r_sub;
+    const uint64_t group = ((uint64_t)row * (uint64_t)p.n + (uint64_t)col) >> 3;
+    const uint4 b = dropout_bits8_call(p.drop.seed_lo, p.drop.seed_hi, p.drop_stream, (uint32_t)group,
+                                       (uint32_t)(group >> 32));
+    const uint32_t r0 = __shfl_xor_sync(0xffffffffu, odd ? b.x : b.z, 1);
+    const uint32_t r1 = __shfl_xor_sync(0xffffffffu, odd ? b.y : b.w, 1);
+    w[pp] = odd ? make_uint2(r0, r1) : make_uint2(b.x, b.y);
+    w[pp + 1] = odd ? make_uint2(b.z, b.w) : make_uint2(r0, r1);
+  }
+}
+__device__ __forceinline__ bool keep4(const uint2& w, int i, uint32_t thr) {
+  const uint32_t v = (i < 2) ? w.x : w.y;
+  return ((i & 1) ? (v >> 16) : (v & 0xffffu)) >= thr;
+}
+
+// epilogue of 4 consecutive columns of one row; `w` = the 4 x 16 dropout bits of these elements
+template <int EPI>
+__device__ __forceinline__ void epilogue4(const GemmKernelParams& p, int row, int col, float4 acc, const float4& bias,
+                                          const float4& resid, const uint2& aux, const uint2& w, bool store) {
   float f[4] = {acc.x, acc.y, acc.z, acc.w};
+  const uint32_t thr = p.drop.thr;
+  const float scale = p.drop.scale;  // 1.0f when dropout is off
 
   if constexpr (EPI == B200B_EPI_BF16_BIAS || EPI == B200B_EPI_BF16_BIAS_GELU ||
                 EPI == B200B_EPI_F32_BIAS_RESID) {
-    if (p.bias != nullptr) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-      f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-    }
-  }
-
-  uint4 bits = make_uint4(0, 0, 0, 0);
-  const bool use_drop = (EPI == B200B_EPI_BF16_BIAS_GELU || EPI == B200B_EPI_F32_BIAS_RESID ||
-                         EPI == B200B_EPI_BF16_DGELU) &&
-                        p.drop.thr != 0;
-  const int e0 = col & 4;  // position of these 4 columns inside their 8-element dropout group
-  if (use_drop) {
-    const uint64_t group = ((uint64_t)row * (uint64_t)p.n + (uint64_t)col) >> 3;
-    bits = dropout_bits8(p.drop, p.drop_stream, group);
+    f[0] += bias.x; f[1] += bias.y; f[2] += bias.z; f[3] += bias.w;
   }
 
   if constexpr (EPI == B200B_EPI_BF16_BIAS) {
     uint2 o;
     o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col) = o;
+    if (store) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col) = o;
   } else if constexpr (EPI == B200B_EPI_BF16_BIAS_GELU) {
     float h[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       f[i] = bf16_round(f[i]);          // the reference Linear output is bf16 under autocast
       h[i] = bf16_round(gelu_erf(f[i]));
-      if (use_drop) h[i] = dropout_keep(bits, e0 + i, p.drop.thr) ? h[i] * p.drop.scale : 0.0f;
+      h[i] = keep4(w, i, thr) ? h[i] * scale : 0.0f;
     }
     uint2 u, o;
     u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]);
     o.x = pack_bf16(h[0], h[1]); o.y = pack_bf16(h[2], h[3]);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.aux) + (long long)row * p.ldaux + col) = u;
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col) = o;
+    if (store) {
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.aux) + (long long)row * p.ldaux + col) = u;
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col) = o;
+    }
   } else if constexpr (EPI == B200B_EPI_F32_BIAS_RESID) {
-    const float4 r0 = *reinterpret_cast<const float4*>(p.resid + (long long)row * p.ldr + col);
-    const float r[4] = {r0.x, r0.y, r0.z, r0.w};
+    const float r[4] = {resid.x, resid.y, resid.z, resid.w};
     float o[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float y = bf16_round(f[i]);
-      if (use_drop) y = dropout_keep(bits, e0 + i, p.drop.thr) ? bf16_round(y * p.drop.scale) : 0.0f;
+      if (thr != 0) y = keep4(w, i, thr) ? bf16_round(y * scale) : 0.0f;
       o[i] = r[i] + y;
     }
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col) =
-        make_float4(o[0], o[1], o[2], o[3]);
+    if (store)
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col) =
+          make_float4(o[0], o[1], o[2], o[3]);
   } else if constexpr (EPI == B200B_EPI_BF16_DGELU) {
-    const uint2 uu = *reinterpret_cast<const uint2*>(
-        reinterpret_cast<const __nv_bfloat16*>(p.aux) + (long long)row * p.ldaux + col);
-    const float u[4] = {bf16_lo(uu.x), bf16_hi(uu.x), bf16_lo(uu.y), bf16_hi(uu.y)};
+    const float u[4] = {bf16_lo(aux.x), bf16_hi(aux.x), bf16_lo(aux.y), bf16_hi(aux.y)};
     float g[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float d = bf16_round(f[i]);
-      if (use_drop) d = dropout_keep(bits, e0 + i, p.drop.thr) ? bf16_round(d * p.drop.scale) : 0.0f;
+      if (thr != 0) d = keep4(w, i, thr) ? bf16_round(d * scale) : 0.0f;
       g[i] = d * gelu_erf_grad(u[i]);
     }
     uint2 o;
     o.x = pack_bf16(g[0], g[1]); o.y = pack_bf16(g[2], g[3]);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col) = o;
+    if (store) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col) = o;
   } else {  // B200B_EPI_F32
     float* op = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col;
-    if (p.beta != 0.0f) {
-      const float4 o0 = *reinterpret_cast<const float4*>(op);
-      f[0] += p.beta * o0.x; f[1] += p.beta * o0.y; f[2] += p.beta * o0.z; f[3] += p.beta * o0.w;
+    if (store) {
+      if (p.beta != 0.0f) {
+        const float4 o0 = *reinterpret_cast<const float4*>(op);
+        f[0] += p.beta * o0.x; f[1] += p.beta * o0.y; f[2] += p.beta * o0.z; f[3] += p.beta * o0.w;
+      }
+      *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
     }
-    *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
   }
 }
 
@@ -143,32 +224,60 @@ __device__ __forceinline__ void epilogue4(const GemmKernelParams& p, int row, in
 // 32 x 32 chunk through a private padded shared-memory tile so that 8 consecutive lanes own one
 // row's 32 columns (4 each): every global load/store instruction then covers 4 full 128-byte
 // (fp32) or 64-byte (bf16) row segments.
+// Two warps serve each TMEM lane quadrant: warp `half` (0/1) takes the 32-column chunks
+// half, half+2, ... of the tile.
 constexpr int kEpiLd = 33;                                  // padded row, words (conflict free both ways)
 constexpr uint32_t kEpiBytesPerWarp = 32 * kEpiLd * 4;      // 4224 B
-constexpr uint32_t kEpiBytes = 4 * kEpiBytesPerWarp;
+constexpr uint32_t kEpiBytes = kEpiWarps * kEpiBytesPerWarp;
+
+// The tile's first group of epilogue operands: issued BEFORE waiting for the accumulator.
+template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void drain_prefetch(const GemmKernelParams& p, int row0, int n_idx, int half, int lane,
+                                               EpiOperands<EPI>& ops) {
+  epi_fetch<EPI>(p, row0, n_idx + 32 * half + 4 * (lane & 7), lane >> 3, ops);
+}
 
 template <int BLOCK_N, int EPI>
 __device__ __forceinline__ void drain_accumulator(const GemmKernelParams& p, uint32_t t_row, int row0 /*of this warp*/,
-                                                  int n_idx, float* stage /*this warp's tile*/, int lane) {
+                                                  int n_idx, float* stage /*this warp's tile*/, int lane, int half,
+                                                  EpiOperands<EPI>& ops /*prefetched for the first group*/) {
   const int r_sub = lane >> 3, cg = lane & 7;
+  constexpr int kChunks = BLOCK_N / 64;  // chunks per warp
 #pragma unroll 1
-  for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+  for (int i = 0; i < kChunks; ++i) {
+    const int c0 = 32 * (2 * i + half);
     if (n_idx + c0 >= p.n) break;  // warp-uniform
-    uint32_t v[32];
-    tmem_ld_32x32(t_row + (uint32_t)c0, v);
-    tmem_ld_wait();
+    {
+      uint32_t v[32];
+      tmem_ld_32x32(t_row + (uint32_t)c0, v);
+      tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) stage[lane * kEpiLd + j] = __uint_as_float(v[j]);
+      for (int j = 0; j < 32; ++j) stage[lane * kEpiLd + j] = __uint_as_float(v[j]);
+    }
     __syncwarp();
     const int col = n_idx + c0 + 4 * cg;
-    if (col < p.n) {
+#pragma unroll 1
+    for (int grp = 0; grp < 8 / kGroupPasses; ++grp) {
+      const int grow0 = row0 + 4 * kGroupPasses * grp;
+      // operands of the next group: same chunk, next 16 rows -- or the first 16 rows of this warp's next chunk
+      EpiOperands<EPI> nxt;
+      {
+        const bool last_grp = grp == 8 / kGroupPasses - 1;
+        const int nrow0 = last_grp ? row0 : grow0 + 4 * kGroupPasses;
+        const int ncol = last_grp ? col + 64 : col;
+        if (!(last_grp && i + 1 == kChunks)) epi_fetch<EPI>(p, nrow0, ncol, r_sub, nxt);
+      }
+      uint2 w[kGroupPasses];
+      if constexpr (kEpiHasDropout<EPI>) epi_dropout_bits(p, grow0, col, r_sub, cg, w);
 #pragma unroll
-      for (int pass = 0; pass < 8; ++pass) {
-        const int r = 4 * pass + r_sub;
+      for (int pass = 0; pass < kGroupPasses; ++pass) {
+        const int r = 4 * (kGroupPasses * grp + pass) + r_sub;
         const float* sp = stage + r * kEpiLd + 4 * cg;
         const float4 acc = make_float4(sp[0], sp[1], sp[2], sp[3]);
-        if (row0 + r < p.m) epilogue4<EPI>(p, row0 + r, col, acc);
+        epilogue4<EPI>(p, row0 + r, col, acc, ops.bias, ops.resid[pass], ops.aux[pass], w[pass],
+                       col < p.n && row0 + r < p.m);
       }
+      ops = nxt;
     }
     __syncwarp();
   }
@@ -207,7 +316,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
   const uint32_t tfull0 = smem_u32(tmem_full_bar), tempty0 = smem_u32(tmem_empty_bar);
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
 #pragma unroll
@@ -217,11 +326,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     mbar_init(&tmem_full_bar[0], 1);
     mbar_init(&tmem_full_bar[1], 1);
-    mbar_init(&tmem_empty_bar[0], 128);
-    mbar_init(&tmem_empty_bar[1], 128);
+    mbar_init(&tmem_empty_bar[0], 32 * kEpiWarps);
+    mbar_init(&tmem_empty_bar[1], 32 * kEpiWarps);
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc(&tmem_base_smem, Cfg::kTmemCols);
     tmem_relinquish();
   }
@@ -231,7 +340,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   const uint32_t tmem_base = tmem_base_smem;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ------------------------------- TMA producer -------------------------------------------
     int stage = 0;
     uint32_t phase = 0;
@@ -269,7 +378,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------- MMA issuer ---------------------------------------------
     constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, A_MN, B_MN);
     // K-major: 8-row groups 1024 B apart; advancing 16 k elements = +32 B inside the swizzle row.
@@ -308,17 +417,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   } else {
     // ------------------------------- epilogue -----------------------------------------------
     const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are visible to this warp
-    float* epi_stage = reinterpret_cast<float*>(smem_gen + (size_t)kStages * Cfg::kStageBytes) + quad * 32 * kEpiLd;
+    const int half = warp >> 2;
+    float* epi_stage =
+        reinterpret_cast<float*>(smem_gen + (size_t)kStages * Cfg::kStageBytes) + warp * 32 * kEpiLd;
     int iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       const int m_idx = (tile % p.num_m_blocks) * kBlockM;
       const int n_idx = (tile / p.num_m_blocks) * BLOCK_N;
+      EpiOperands<EPI> ops;
+      drain_prefetch<BLOCK_N, EPI>(p, m_idx + quad * 32, n_idx, half, lane, ops);
       mbar_wait_a(tfull0 + 8u * acc, acc_phase);
       tc_fence_after();
       drain_accumulator<BLOCK_N, EPI>(p, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N),
-                                      m_idx + quad * 32, n_idx, epi_stage, lane);
+                                      m_idx + quad * 32, n_idx, epi_stage, lane, half, ops);
       tc_fence_before();
       mbar_arrive_a(tempty0 + 8u * acc);
     }
@@ -326,7 +439,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
 // ================================================================================================
@@ -379,7 +492,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   const uint32_t full0_even = full0 & 0xFEFFFFFFu;          // same offset in the pair's even CTA
   const uint32_t tempty0_even = mapa_u32(tempty0, 0);
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
 #pragma unroll
@@ -389,11 +502,11 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     }
     mbar_init(&tmem_full_bar[0], 1);
     mbar_init(&tmem_full_bar[1], 1);
-    mbar_init(&tmem_empty_bar[0], 256);
-    mbar_init(&tmem_empty_bar[1], 256);
+    mbar_init(&tmem_empty_bar[0], 2 * 32 * kEpiWarps);   // local + remote epilogue threads
+    mbar_init(&tmem_empty_bar[1], 2 * 32 * kEpiWarps);
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc_pair(&tmem_base_smem, Cfg::kTmemCols);
     tmem_relinquish_pair();
   }
@@ -403,7 +516,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   const uint32_t tmem_base = tmem_base_smem;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;  // num_m_blocks counts 256-row pair tiles
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ------------------------------- TMA producer (both CTAs) --------------------------------
     int stage = 0;
     uint32_t phase = 0;
@@ -435,7 +548,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------- MMA issuer (even CTA only) ------------------------------
     if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * kBlockM, BLOCK_N, A_MN, B_MN);
@@ -472,17 +585,21 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   } else {
     // ------------------------------- epilogue (both CTAs, own 128 rows) ----------------------
     const int quad = warp & 3;
-    float* epi_stage = reinterpret_cast<float*>(smem_gen + (size_t)kStages * Cfg::kStageBytes) + quad * 32 * kEpiLd;
+    const int half = warp >> 2;
+    float* epi_stage =
+        reinterpret_cast<float*>(smem_gen + (size_t)kStages * Cfg::kStageBytes) + warp * 32 * kEpiLd;
     int iter = 0;
     for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       const int m_idx = (tile % p.num_m_blocks) * (2 * kBlockM) + (int)cta_rank * kBlockM;
       const int n_idx = (tile / p.num_m_blocks) * BLOCK_N;
+      EpiOperands<EPI> ops;
+      drain_prefetch<BLOCK_N, EPI>(p, m_idx + quad * 32, n_idx, half, lane, ops);
       mbar_wait_a(tfull0 + 8u * acc, acc_phase);
       tc_fence_after();
       drain_accumulator<BLOCK_N, EPI>(p, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N),
-                                      m_idx + quad * 32, n_idx, epi_stage, lane);
+                                      m_idx + quad * 32, n_idx, epi_stage, lane, half, ops);
       tc_fence_before();
       mbar_arrive_cluster_a(tempty0_even + 8u * acc);  // the even CTA's MMA thread owns the accumulator handshake
     }
@@ -490,7 +607,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 
   tc_fence_before();
   cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still touch its smem / barriers
-  if (warp == 1) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+  if (warp == kMmaWarp) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------
