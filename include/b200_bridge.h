@@ -135,6 +135,40 @@ int b200b_cast_bf16(const float* in, void* out_bf16, int64_t n, float dropout_p,
                     uint32_t dropout_stream, void* stream);
 
 /* ------------------------------------------------------------------------------------------- *
+ * CTA-per-row variants used by the whole-block entry points: same arithmetic as the kernels
+ * above, one pass over each row, column reductions emitted as per-CTA partials that a single
+ * b200b_colsum_finalize launch reduces (deterministic order).
+ * ------------------------------------------------------------------------------------------- */
+#define B200B_MAX_COLSUM_TASKS 16
+typedef struct b200b_colsum_task {
+  const float* partials; /* [chunks][chunk_stride] */
+  float* out;            /* [cols] = sum over chunks of partials[j*chunk_stride + c] */
+  int32_t cols, chunks;
+  int64_t chunk_stride;
+} b200b_colsum_task;
+
+/* number of CTAs (= partial chunks) the row kernels below use for `rows` rows on this device */
+int b200b_row_chunks(int rows);
+/* as b200b_layernorm_fwd */
+int b200b_layernorm_fwd_rows(const float* x, const float* gamma, const float* beta, void* y_bf16,
+                             float* mean, float* rstd, int rows, int dim, float eps, void* stream);
+/* LayerNorm input gradient (as b200b_layernorm_bwd) fused with the bf16 cast of dx (dy_next, may be
+ * NULL) and three column reductions written to partials[b200b_row_chunks(rows)][3][dim]:
+ * [0] sum dy (dbeta), [1] sum dy*xhat (dgamma), [2] sum dy_next (bias gradient of the preceding
+ * output projection). dx may be NULL (then dy_next must be NULL): only [0], [1] are meaningful. */
+int b200b_layernorm_bwd_fused(const void* dy_bf16, const float* x, const float* mean, const float* rstd,
+                              const float* gamma, const float* dres, float* dx, void* dy_next_bf16,
+                              float* partials, int rows, int dim, void* stream);
+/* b200b_cast_bf16 over a [rows, dim] matrix fused with the column sums of its bf16 result:
+ * partials[b200b_row_chunks(rows)][dim]. dim % 8 == 0, dim <= 9216. */
+int b200b_cast_bf16_colsum(const float* in, void* out_bf16, float* partials, int rows, int dim,
+                           float dropout_p, uint64_t seed, uint32_t dropout_stream, void* stream);
+/* first stage of b200b_colsum (plain column sums): partials[*chunks_out][cols], *chunks_out <= 64 */
+int b200b_colsum_partials(const void* dy_bf16, int64_t ld, int rows, int cols, float* partials,
+                          int* chunks_out, void* stream);
+int b200b_colsum_finalize(const b200b_colsum_task* tasks, int ntasks, void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
  * Fused multi-head attention, softmax(Q K^T / sqrt(d)) V, no mask, non-causal.
  * Replaces F.scaled_dot_product_attention (bridge_module.py:132-139, 230-237) and the head
  * split / merge around it (:103-115, :201-213): token t = b*len + i of head h is read at

@@ -65,16 +65,26 @@ def run_case(i: int) -> dict:
         d2 = dres.clone()
         ops.layernorm_bwd(dy, x, mean, rstd, g, d2, out=d2)
         e_alias = relerr(d2, dx)
-        res.update(e_y=e_y, e_dx=e_dx, e_dgamma=e_dg, e_dbeta=e_db, e_alias=e_alias)
-        res["ok"] = e_y < 6e-3 and e_dx < 1e-4 and e_dg < 1e-4 and e_db < 1e-4 and e_alias == 0
+        # CTA-per-row variants used by the whole-block entry points
+        y2, mean2, rstd2 = ops.layernorm_fwd_rows(x, g, b)
+        e_rows = max(relerr(y2, yr.detach()), relerr(mean2, mean), relerr(rstd2, rstd))
+        fdx, fdy, fdb, fdg, fcs = ops.layernorm_bwd_fused(dy, x, mean, rstd, g, dres)
+        e_f = max(relerr(fdx, xr.grad + dres), relerr(fdg, gr.grad), relerr(fdb, br.grad),
+                  relerr(fdy, (xr.grad + dres).bfloat16()), relerr(fcs, fdy.float().sum(0)))
+        _, _, fdb2, fdg2, _ = ops.layernorm_bwd_fused(dy, x, mean, rstd, g, None, want_dx=False)
+        e_f = max(e_f, relerr(fdg2, gr.grad), relerr(fdb2, br.grad))
+        res.update(e_y=e_y, e_dx=e_dx, e_dgamma=e_dg, e_dbeta=e_db, e_alias=e_alias, e_rows=e_rows, e_fused=e_f)
+        res["ok"] = (e_y < 6e-3 and e_dx < 1e-4 and e_dg < 1e-4 and e_db < 1e-4 and e_alias == 0 and e_rows < 6e-3
+                     and e_f < 8e-3)
     elif c[0] == "colsum":
         _, rows, cols = c
         big = torch.randn(rows, cols + 64, device=dev).bfloat16()
         dy = big[:, :cols]  # pitched view
         s = ops.colsum(dy)
         e = relerr(s, dy.float().sum(0))
-        res.update(e=e)
-        res["ok"] = e < 1e-4
+        e2 = relerr(ops.colsum_two_stage(dy), dy.float().sum(0))
+        res.update(e=e, e_two_stage=e2)
+        res["ok"] = e < 1e-4 and e2 < 1e-4
     elif c[0] == "cast":
         _, n, p = c
         x = torch.randn(n, device=dev)
@@ -96,6 +106,11 @@ def run_case(i: int) -> dict:
                          dropout_stream=4)
             res["mask_matches_gemm"] = bool(torch.equal(o.reshape(-1) != 0, keep))
             res["ok"] = res["ok"] and res["mask_matches_gemm"]
+            # fused cast + column sums (the block backward's first kernel): same bytes, same mask
+            y2, cs = ops.cast_bf16_colsum(x.view(M, N), dropout_p=p, seed=99, dropout_stream=4)
+            res["fused_equal"] = bool(torch.equal(y2.reshape(-1), y))
+            res["e_colsum"] = relerr(cs, y2.float().sum(0))
+            res["ok"] = res["ok"] and res["fused_equal"] and res["e_colsum"] < 1e-4
     else:
         _, B, H, Lq, Lk, d, p = c
         D = H * d

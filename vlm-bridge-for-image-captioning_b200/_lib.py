@@ -49,6 +49,11 @@ class GemmArgs(C.Structure):
     ]
 
 
+class ColsumTask(C.Structure):
+    _fields_ = [("partials", C.c_void_p), ("out", C.c_void_p), ("cols", C.c_int32), ("chunks", C.c_int32),
+                ("chunk_stride", C.c_int64)]
+
+
 class AttnArgs(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("ldq", C.c_int64),
@@ -101,6 +106,20 @@ def _declare(lib) -> None:
     lib.b200b_cast_bf16.restype = C.c_int
     lib.b200b_cast_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_uint64, C.c_uint32,
                                     C.c_void_p]
+    lib.b200b_row_chunks.restype = C.c_int
+    lib.b200b_row_chunks.argtypes = [C.c_int]
+    lib.b200b_layernorm_fwd_rows.restype = C.c_int
+    lib.b200b_layernorm_fwd_rows.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_float, C.c_void_p]
+    lib.b200b_layernorm_bwd_fused.restype = C.c_int
+    lib.b200b_layernorm_bwd_fused.argtypes = [C.c_void_p] * 9 + [C.c_int, C.c_int, C.c_void_p]
+    lib.b200b_cast_bf16_colsum.restype = C.c_int
+    lib.b200b_cast_bf16_colsum.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_float, C.c_uint64, C.c_uint32,
+                                           C.c_void_p]
+    lib.b200b_colsum_partials.restype = C.c_int
+    lib.b200b_colsum_partials.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int),
+                                          C.c_void_p]
+    lib.b200b_colsum_finalize.restype = C.c_int
+    lib.b200b_colsum_finalize.argtypes = [C.POINTER(ColsumTask), C.c_int, C.c_void_p]
     lib.b200b_attention_fwd.restype = C.c_int
     lib.b200b_attention_fwd.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
     lib.b200b_attention_bwd_workspace_bytes.restype = C.c_size_t

@@ -91,11 +91,13 @@ static Saved carve_saved(const Dims& d, void* base) {
 }
 
 // transient buffers of the backward pass
+constexpr int kMaxRowChunks = 320;  // >= 2 x SM count: upper bound of b200b_row_chunks()
 struct BwdWs {
   __nv_bfloat16 *dy, *du, *dxn, *dattn, *dqkv;
   float* dx;
   uint8_t* attn_ws; size_t attn_ws_bytes;
-  uint8_t* colsum_ws; size_t colsum_ws_bytes;
+  // per-CTA partial column sums, finished by ONE b200b_colsum_finalize launch per block
+  float *p_cast, *p_du, *p_lnf, *p_dqkv, *p_lns, *p_dq, *p_lnc, *p_dkv;
   size_t bytes;
 };
 
@@ -113,14 +115,29 @@ static BwdWs carve_bwd(const Dims& d, void* base) {
   const size_t a2 = b200b_attention_bwd_workspace_bytes(d.B, d.Hs, d.L, d.L);
   w.attn_ws_bytes = a1 > a2 ? a1 : a2;
   w.attn_ws = c.take<uint8_t>(w.attn_ws_bytes);
-  int maxc = d.F;
-  if (3 * d.D > maxc) maxc = 3 * d.D;
-  if (2 * d.D * d.nb > maxc) maxc = 2 * d.D * d.nb;
-  w.colsum_ws_bytes = b200b_colsum_workspace_bytes(0, maxc);
-  w.colsum_ws = c.take<uint8_t>(w.colsum_ws_bytes);
+  const size_t rc = d.T < (size_t)kMaxRowChunks ? d.T : (size_t)kMaxRowChunks;  // row-kernel chunks
+  const size_t D = d.D;
+  w.p_cast = c.take<float>(rc * D);
+  w.p_du = c.take<float>((size_t)64 * d.F);
+  w.p_lnf = c.take<float>(rc * 3 * D);
+  w.p_dqkv = c.take<float>((size_t)64 * 3 * D);
+  w.p_lns = c.take<float>(rc * 3 * D);
+  w.p_dq = c.take<float>((size_t)64 * D);
+  w.p_lnc = c.take<float>(rc * 3 * D);
+  w.p_dkv = c.take<float>((size_t)64 * 2 * D * d.nb);
   w.bytes = c.off;
   return w;
 }
+
+// list of partial column-sum sets to be finished at the end of a block's backward
+struct Finalizer {
+  b200b_colsum_task t[B200B_MAX_COLSUM_TASKS];
+  int n = 0;
+  void add(const float* partials, float* out, int cols, int chunks, long long stride) {
+    t[n].partials = partials; t[n].out = out; t[n].cols = cols; t[n].chunks = chunks; t[n].chunk_stride = stride;
+    ++n;
+  }
+};
 
 #define B200B_TRY(expr)        \
   do {                         \
@@ -214,7 +231,7 @@ extern "C" int b200b_bridge_block_forward(const b200b_bridge_dims* dims, int i, 
   const float eps = 1e-5f;
 
   // 1. cross-attention: x1 = x + W_o * SDPA(W_q * LN(x), K_i, V_i)          (bridge_module.py:316-323)
-  B200B_TRY(b200b_layernorm_fwd(x_in, w->ln_c_g, w->ln_c_b, s.xn1, s.mean1, s.rstd1, T, D, eps, st));
+  B200B_TRY(b200b_layernorm_fwd_rows(x_in, w->ln_c_g, w->ln_c_b, s.xn1, s.mean1, s.rstd1, T, D, eps, st));
   B200B_TRY(gemm(s.xn1, 0, D, w->wq_c, 0, D, T, D, D, B200B_EPI_BF16_BIAS, s.q, D, w->bq_c, nullptr, nullptr, 0, 0.f, 0,
                  0, st));
   B200B_TRY(attn(false, s.q, D, kblk, ldkv, kblk + D, ldkv, s.o1, D, s.lse1, nullptr, nullptr, 0, nullptr, 0, nullptr, 0,
@@ -222,7 +239,7 @@ extern "C" int b200b_bridge_block_forward(const b200b_bridge_dims* dims, int i, 
   B200B_TRY(gemm(s.o1, 0, D, w->wo_c, 0, D, T, D, D, B200B_EPI_F32_BIAS_RESID, s.x1, D, w->bo_c, x_in, nullptr, 0, 0.f,
                  0, 0, st));
   // 2. self-attention (non-causal, unmasked)                                 (:326-328)
-  B200B_TRY(b200b_layernorm_fwd(s.x1, w->ln_s_g, w->ln_s_b, s.xn2, s.mean2, s.rstd2, T, D, eps, st));
+  B200B_TRY(b200b_layernorm_fwd_rows(s.x1, w->ln_s_g, w->ln_s_b, s.xn2, s.mean2, s.rstd2, T, D, eps, st));
   B200B_TRY(gemm(s.xn2, 0, D, w->wqkv_s, 0, D, T, 3 * D, D, B200B_EPI_BF16_BIAS, s.qkv, 3 * D, w->bqkv_s, nullptr,
                  nullptr, 0, 0.f, 0, 0, st));
   B200B_TRY(attn(false, s.qkv, 3 * D, s.qkv + D, 3 * D, s.qkv + 2 * D, 3 * D, s.o2, D, s.lse2, nullptr, nullptr, 0,
@@ -230,7 +247,7 @@ extern "C" int b200b_bridge_block_forward(const b200b_bridge_dims* dims, int i, 
   B200B_TRY(gemm(s.o2, 0, D, w->wo_s, 0, D, T, D, D, B200B_EPI_F32_BIAS_RESID, s.x2, D, w->bo_s, s.x1, nullptr, 0, 0.f,
                  0, 0, st));
   // 3. FFN: x3 = x2 + drop(W_2 * drop(gelu(W_1 * LN(x2))))                    (:331-333)
-  B200B_TRY(b200b_layernorm_fwd(s.x2, w->ln_f_g, w->ln_f_b, s.xn3, s.mean3, s.rstd3, T, D, eps, st));
+  B200B_TRY(b200b_layernorm_fwd_rows(s.x2, w->ln_f_g, w->ln_f_b, s.xn3, s.mean3, s.rstd3, T, D, eps, st));
   B200B_TRY(gemm(s.xn3, 0, D, w->w1, 0, D, T, F, D, B200B_EPI_BF16_BIAS_GELU, s.h, F, w->b1, nullptr, s.u, F, p, seed,
                  ds_ffn_h(i), st));
   B200B_TRY(gemm(s.h, 0, F, w->w2, 0, F, T, D, F, B200B_EPI_F32_BIAS_RESID, x_out, D, w->b2, s.x2, nullptr, 0, p, seed,
@@ -261,51 +278,61 @@ extern "C" int b200b_bridge_block_backward(const b200b_bridge_dims* dims, int i,
   __nv_bfloat16* dkblk = reinterpret_cast<__nv_bfloat16*>(dkv) + (size_t)2 * D * i;
   const int EB = B200B_EPI_BF16_BIAS, EF = B200B_EPI_F32;
 
+  const int rchunks = b200b_row_chunks(T);
+  if (rchunks <= 0 || rchunks > kMaxRowChunks) {
+    set_last_error("block_backward: no usable device (row chunks = %d)", rchunks);
+    return B200B_ERR_DEVICE;
+  }
+  Finalizer fin;
+  int ch = 0;
+
   // ---- FFN ----
-  B200B_TRY(b200b_cast_bf16(d_out, ws.dy, (int64_t)T * D, p, seed, ds_ffn_o(i), st));  // d(ffn.3 out), dropout bwd
-  B200B_TRY(b200b_colsum(ws.dy, D, nullptr, nullptr, nullptr, g->b2, nullptr, T, D, ws.colsum_ws, ws.colsum_ws_bytes, st));
+  // d(ffn.3 out) = dropout-bwd(bf16(d_out)); its column sums are the ffn.3 bias gradient
+  B200B_TRY(b200b_cast_bf16_colsum(d_out, ws.dy, ws.p_cast, T, D, p, seed, ds_ffn_o(i), st));
+  fin.add(ws.p_cast, g->b2, D, rchunks, D);
   B200B_TRY(gemm(ws.dy, 1, D, s.h, 1, F, D, F, T, EF, g->w2, F, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
   B200B_TRY(gemm(ws.dy, 0, D, w->w2, 1, F, T, F, D, B200B_EPI_BF16_DGELU, ws.du, F, nullptr, nullptr, s.u, F, p, seed,
                  ds_ffn_h(i), st));
-  B200B_TRY(b200b_colsum(ws.du, F, nullptr, nullptr, nullptr, g->b1, nullptr, T, F, ws.colsum_ws, ws.colsum_ws_bytes, st));
+  B200B_TRY(b200b_colsum_partials(ws.du, F, T, F, ws.p_du, &ch, st));
+  fin.add(ws.p_du, g->b1, F, ch, F);
   B200B_TRY(gemm(ws.du, 1, F, s.xn3, 1, D, F, D, T, EF, g->w1, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
   B200B_TRY(gemm(ws.du, 0, F, w->w1, 1, D, T, D, F, EB, ws.dxn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
-  B200B_TRY(b200b_layernorm_bwd(ws.dxn, s.x2, s.mean3, s.rstd3, w->ln_f_g, d_out, ws.dx, T, D, st));
-  B200B_TRY(b200b_colsum(ws.dxn, D, s.x2, s.mean3, s.rstd3, g->ln_f_b, g->ln_f_g, T, D, ws.colsum_ws, ws.colsum_ws_bytes,
-                         st));
+  // ln_ffn backward (+ residual gradient d_out) -> dx; bf16(dx) = gradient of the self-attention W_o output
+  B200B_TRY(b200b_layernorm_bwd_fused(ws.dxn, s.x2, s.mean3, s.rstd3, w->ln_f_g, d_out, ws.dx, ws.dy, ws.p_lnf, T, D, st));
+  fin.add(ws.p_lnf, g->ln_f_b, D, rchunks, 3LL * D);
+  fin.add(ws.p_lnf + D, g->ln_f_g, D, rchunks, 3LL * D);
+  fin.add(ws.p_lnf + 2 * D, g->bo_s, D, rchunks, 3LL * D);
   // ---- self-attention ----
-  B200B_TRY(b200b_cast_bf16(ws.dx, ws.dy, (int64_t)T * D, 0.f, 0, 0, st));
-  B200B_TRY(b200b_colsum(ws.dy, D, nullptr, nullptr, nullptr, g->bo_s, nullptr, T, D, ws.colsum_ws, ws.colsum_ws_bytes, st));
   B200B_TRY(gemm(ws.dy, 1, D, s.o2, 1, D, D, D, T, EF, g->wo_s, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
   B200B_TRY(gemm(ws.dy, 0, D, w->wo_s, 1, D, T, D, D, EB, ws.dattn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
   B200B_TRY(attn(true, s.qkv, 3 * D, s.qkv + D, 3 * D, s.qkv + 2 * D, 3 * D, s.o2, D, s.lse2, ws.dattn, ws.dqkv, 3 * D,
                  ws.dqkv + D, 3 * D, ws.dqkv + 2 * D, 3 * D, ws.attn_ws, ws.attn_ws_bytes, d.B, d.Hs, d.L, d.L, d.ds, p,
                  seed, ds_self(i), st));
-  B200B_TRY(b200b_colsum(ws.dqkv, 3 * D, nullptr, nullptr, nullptr, g->bqkv_s, nullptr, T, 3 * D, ws.colsum_ws,
-                         ws.colsum_ws_bytes, st));
+  B200B_TRY(b200b_colsum_partials(ws.dqkv, 3 * D, T, 3 * D, ws.p_dqkv, &ch, st));
+  fin.add(ws.p_dqkv, g->bqkv_s, 3 * D, ch, 3LL * D);
   B200B_TRY(gemm(ws.dqkv, 1, 3 * D, s.xn2, 1, D, 3 * D, D, T, EF, g->wqkv_s, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0,
                  st));
   B200B_TRY(gemm(ws.dqkv, 0, 3 * D, w->wqkv_s, 1, D, T, D, 3 * D, EB, ws.dxn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0,
                  st));
-  B200B_TRY(b200b_layernorm_bwd(ws.dxn, s.x1, s.mean2, s.rstd2, w->ln_s_g, ws.dx, ws.dx, T, D, st));
-  B200B_TRY(b200b_colsum(ws.dxn, D, s.x1, s.mean2, s.rstd2, g->ln_s_b, g->ln_s_g, T, D, ws.colsum_ws, ws.colsum_ws_bytes,
-                         st));
+  B200B_TRY(b200b_layernorm_bwd_fused(ws.dxn, s.x1, s.mean2, s.rstd2, w->ln_s_g, ws.dx, ws.dx, ws.dy, ws.p_lns, T, D, st));
+  fin.add(ws.p_lns, g->ln_s_b, D, rchunks, 3LL * D);
+  fin.add(ws.p_lns + D, g->ln_s_g, D, rchunks, 3LL * D);
+  fin.add(ws.p_lns + 2 * D, g->bo_c, D, rchunks, 3LL * D);
   // ---- cross-attention ----
-  B200B_TRY(b200b_cast_bf16(ws.dx, ws.dy, (int64_t)T * D, 0.f, 0, 0, st));
-  B200B_TRY(b200b_colsum(ws.dy, D, nullptr, nullptr, nullptr, g->bo_c, nullptr, T, D, ws.colsum_ws, ws.colsum_ws_bytes, st));
   B200B_TRY(gemm(ws.dy, 1, D, s.o1, 1, D, D, D, T, EF, g->wo_c, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
   B200B_TRY(gemm(ws.dy, 0, D, w->wo_c, 1, D, T, D, D, EB, ws.dattn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
   __nv_bfloat16* dq = ws.dqkv;  // [T, D]
   B200B_TRY(attn(true, s.q, D, kblk, ldkv, kblk + D, ldkv, s.o1, D, s.lse1, ws.dattn, dq, D, dkblk, ldkv, dkblk + D, ldkv,
                  ws.attn_ws, ws.attn_ws_bytes, d.B, d.Hc, d.L, d.Nv, d.dc, p, seed, ds_cross(i), st));
-  B200B_TRY(b200b_colsum(dq, D, nullptr, nullptr, nullptr, g->bq_c, nullptr, T, D, ws.colsum_ws, ws.colsum_ws_bytes, st));
+  B200B_TRY(b200b_colsum_partials(dq, D, T, D, ws.p_dq, &ch, st));
+  fin.add(ws.p_dq, g->bq_c, D, ch, D);
   B200B_TRY(gemm(dq, 1, D, s.xn1, 1, D, D, D, T, EF, g->wq_c, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
   B200B_TRY(gemm(dq, 0, D, w->wq_c, 1, D, T, D, D, EB, ws.dxn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
-  if (d_in != nullptr)
-    B200B_TRY(b200b_layernorm_bwd(ws.dxn, x_in, s.mean1, s.rstd1, w->ln_c_g, ws.dx, d_in, T, D, st));
-  B200B_TRY(b200b_colsum(ws.dxn, D, x_in, s.mean1, s.rstd1, g->ln_c_b, g->ln_c_g, T, D, ws.colsum_ws, ws.colsum_ws_bytes,
-                         st));
-  return B200B_OK;
+  // ln_cross backward: d_in (if wanted) = dx + LN input gradient; dgamma / dbeta always
+  B200B_TRY(b200b_layernorm_bwd_fused(ws.dxn, x_in, s.mean1, s.rstd1, w->ln_c_g, ws.dx, d_in, nullptr, ws.p_lnc, T, D, st));
+  fin.add(ws.p_lnc, g->ln_c_b, D, rchunks, 3LL * D);
+  fin.add(ws.p_lnc + D, g->ln_c_g, D, rchunks, 3LL * D);
+  return b200b_colsum_finalize(fin.t, fin.n, st);
 }
 
 extern "C" int b200b_bridge_kv_backward(const b200b_bridge_dims* dims, const void* vision_bf16, const void* dkv,
@@ -324,8 +351,11 @@ extern "C" int b200b_bridge_kv_backward(const b200b_bridge_dims* dims, const voi
     return B200B_ERR_WORKSPACE;
   }
   const int n = 2 * d.D * d.nb;
-  B200B_TRY(b200b_colsum(dkv, n, nullptr, nullptr, nullptr, dbkv_all, nullptr, (int)d.Tv, n, ws.colsum_ws,
-                         ws.colsum_ws_bytes, st));
+  int ch = 0;
+  B200B_TRY(b200b_colsum_partials(dkv, n, (int)d.Tv, n, ws.p_dkv, &ch, st));
+  b200b_colsum_task t;
+  t.partials = ws.p_dkv; t.out = dbkv_all; t.cols = n; t.chunks = ch; t.chunk_stride = n;
+  B200B_TRY(b200b_colsum_finalize(&t, 1, st));
   return gemm(dkv, 1, n, vision_bf16, 1, d.Dv, n, d.Dv, (int)d.Tv, B200B_EPI_F32, dwkv_all, d.Dv, nullptr, nullptr,
               nullptr, 0, 0.f, 0, 0, st);
 }

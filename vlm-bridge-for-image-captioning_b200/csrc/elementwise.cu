@@ -215,6 +215,283 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
   }
 }
 
+// ================================================================================================
+// CTA-per-row kernels (used by the whole-block entry points). At the bridge's row counts
+// (T = 1024..2048) one warp per row leaves ~7 warps per SM and ~1 TB/s; here a CTA of 192 threads
+// owns a row (3 float4 per thread at D = 2304), rows are strided over the grid, and everything that
+// can be derived from the row while it is in registers is produced in the same pass.
+// ================================================================================================
+constexpr int kRowThreads = 192;
+
+// sum of (a, b) over the CTA; `slot` alternates per row so one __syncthreads per row suffices
+__device__ __forceinline__ float2 block_sum2(float a, float b, float2 (*red)[kRowThreads / 32], int slot) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) red[slot][warp] = make_float2(a, b);
+  __syncthreads();
+  float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int w = 0; w < kRowThreads / 32; ++w) {
+    const float2 v = red[slot][w];
+    t.x += v.x;
+    t.y += v.y;
+  }
+  return t;
+}
+
+template <int VPT>
+__global__ void __launch_bounds__(kRowThreads) layernorm_fwd_row_kernel(const float* __restrict__ x,
+                                                                        const float* __restrict__ gamma,
+                                                                        const float* __restrict__ beta,
+                                                                        __nv_bfloat16* __restrict__ y,
+                                                                        float* __restrict__ mean_out,
+                                                                        float* __restrict__ rstd_out, int rows,
+                                                                        int dim, float eps) {
+  __shared__ float2 red[4][kRowThreads / 32];
+  float4 g[VPT], b[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * kRowThreads + threadIdx.x) * 4;
+    g[i] = c < dim ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    b[i] = c < dim ? __ldg(reinterpret_cast<const float4*>(beta + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  int it = 0;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x, ++it) {
+    const float* xr = x + (size_t)row * dim;
+    float4 v[VPT];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = (i * kRowThreads + threadIdx.x) * 4;
+      v[i] = c < dim ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = block_sum2(s, 0.f, red, (2 * it) & 3).x / (float)dim;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = (i * kRowThreads + threadIdx.x) * 4;
+      if (c < dim) {
+        const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+        q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+      }
+    }
+    const float rstd = rsqrtf(block_sum2(q, 0.f, red, (2 * it + 1) & 3).x / (float)dim + eps);
+    if (threadIdx.x == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+    __nv_bfloat16* yr = y + (size_t)row * dim;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = (i * kRowThreads + threadIdx.x) * 4;
+      if (c < dim) {
+        uint2 o;
+        o.x = pack_bf16((v[i].x - mean) * rstd * g[i].x + b[i].x, (v[i].y - mean) * rstd * g[i].y + b[i].y);
+        o.y = pack_bf16((v[i].z - mean) * rstd * g[i].z + b[i].z, (v[i].w - mean) * rstd * g[i].w + b[i].w);
+        *reinterpret_cast<uint2*>(yr + c) = o;
+      }
+    }
+  }
+}
+
+// LayerNorm backward, fused with what follows it in the bridge's backward pass:
+//   g = dy*gamma ; dx = dres + rstd*(g - mean(g) - xhat*mean(g*xhat))      (input gradient, fp32)
+//   dy_next = bf16(dx)                                                     (operand of the previous sub-layer's GEMMs)
+//   partials[cta][0][c] += dy[r,c]            -> LayerNorm dbeta
+//   partials[cta][1][c] += dy[r,c]*xhat[r,c]  -> LayerNorm dgamma
+//   partials[cta][2][c] += dy_next[r,c]       -> bias gradient of the previous sub-layer's output projection
+// dx / dy_next may be NULL (block 0 when the text embeddings need no gradient): only dgamma/dbeta then.
+template <int VPT>
+struct LnBwdRow {
+  float4 x[VPT], r[VPT];
+  uint2 d[VPT];
+  float mean, rstd;
+};
+
+template <int VPT>
+__device__ __forceinline__ void ln_bwd_load(LnBwdRow<VPT>& o, const __nv_bfloat16* __restrict__ dy,
+                                            const float* __restrict__ x, const float* __restrict__ mean_in,
+                                            const float* __restrict__ rstd_in, const float* dres, bool want_res, int row,
+                                            int dim) {
+  o.mean = mean_in[row];
+  o.rstd = rstd_in[row];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * kRowThreads + threadIdx.x) * 4;
+    o.x[i] = o.r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    o.d[i] = make_uint2(0u, 0u);
+    if (c < dim) {
+      o.x[i] = *reinterpret_cast<const float4*>(x + (size_t)row * dim + c);
+      o.d[i] = *reinterpret_cast<const uint2*>(dy + (size_t)row * dim + c);
+      if (want_res) o.r[i] = *reinterpret_cast<const float4*>(dres + (size_t)row * dim + c);
+    }
+  }
+}
+
+template <int VPT>
+__global__ void __launch_bounds__(kRowThreads) layernorm_bwd_row_kernel(
+    const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean_in,
+    const float* __restrict__ rstd_in, const float* __restrict__ gamma, const float* dres, float* dx,
+    __nv_bfloat16* __restrict__ dy_next, float* __restrict__ partials, int rows, int dim) {
+  __shared__ float2 red[2][kRowThreads / 32];
+  float4 gm[VPT], pb[VPT], pg[VPT], pc[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * kRowThreads + threadIdx.x) * 4;
+    gm[i] = c < dim ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    pb[i] = pg[i] = pc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const bool want_res = dx != nullptr && dres != nullptr;
+  // The next row's operands are in flight while this row is reduced and written. dres may alias dx
+  // (in-place residual gradient): a row is only ever read and written by the CTA that owns it, and
+  // its loads complete before its stores are issued.
+  LnBwdRow<VPT> cur, nxt;
+  int row = blockIdx.x;
+  if (row < rows) ln_bwd_load<VPT>(cur, dy, x, mean_in, rstd_in, dres, want_res, row, dim);
+  int it = 0;
+  for (; row < rows; row += gridDim.x, ++it) {
+    const int nrow = row + gridDim.x;
+    if (nrow < rows) ln_bwd_load<VPT>(nxt, dy, x, mean_in, rstd_in, dres, want_res, nrow, dim);
+    const float mean = cur.mean, rstd = cur.rstd;
+    float4 xh[VPT], g[VPT];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = (i * kRowThreads + threadIdx.x) * 4;
+      xh[i] = g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < dim) {
+        const float4 xv = cur.x[i];
+        const uint2 d = cur.d[i];
+        const float d0 = bf16_lo(d.x), d1 = bf16_hi(d.x), d2 = bf16_lo(d.y), d3 = bf16_hi(d.y);
+        xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        g[i] = make_float4(d0 * gm[i].x, d1 * gm[i].y, d2 * gm[i].z, d3 * gm[i].w);
+        pb[i].x += d0; pb[i].y += d1; pb[i].z += d2; pb[i].w += d3;
+        pg[i].x += d0 * xh[i].x; pg[i].y += d1 * xh[i].y; pg[i].z += d2 * xh[i].z; pg[i].w += d3 * xh[i].w;
+        s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+        s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+      }
+    }
+    if (dx != nullptr) {  // uniform
+      const float2 t = block_sum2(s1, s2, red, it & 1);
+      const float m1 = t.x / (float)dim, m2 = t.y / (float)dim;
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) {
+        const int c = (i * kRowThreads + threadIdx.x) * 4;
+        if (c < dim) {
+          const float4 r = cur.r[i];
+          const float4 o = make_float4(r.x + rstd * (g[i].x - m1 - xh[i].x * m2), r.y + rstd * (g[i].y - m1 - xh[i].y * m2),
+                                       r.z + rstd * (g[i].z - m1 - xh[i].z * m2), r.w + rstd * (g[i].w - m1 - xh[i].w * m2));
+          *reinterpret_cast<float4*>(dx + (size_t)row * dim + c) = o;
+          if (dy_next != nullptr) {
+            uint2 ob;
+            ob.x = pack_bf16(o.x, o.y);
+            ob.y = pack_bf16(o.z, o.w);
+            *reinterpret_cast<uint2*>(dy_next + (size_t)row * dim + c) = ob;
+            pc[i].x += bf16_lo(ob.x); pc[i].y += bf16_hi(ob.x); pc[i].z += bf16_lo(ob.y); pc[i].w += bf16_hi(ob.y);
+          }
+        }
+      }
+    }
+    cur = nxt;
+  }
+  float* pr = partials + (size_t)blockIdx.x * 3 * dim;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * kRowThreads + threadIdx.x) * 4;
+    if (c < dim) {
+      *reinterpret_cast<float4*>(pr + c) = pb[i];
+      *reinterpret_cast<float4*>(pr + dim + c) = pg[i];
+      *reinterpret_cast<float4*>(pr + 2 * dim + c) = pc[i];
+    }
+  }
+}
+
+// fp32 -> bf16 cast of a [rows, dim] matrix with the dropout-backward mask of `stream`
+// (same element indexing as cast_bf16_kernel) fused with the column sums of the bf16 result:
+// partials[cta][c] = sum over this CTA's rows. Thread = one 8-element dropout group per row pass.
+template <int GPT>
+__global__ void __launch_bounds__(288) cast_colsum_row_kernel(const float* __restrict__ in,
+                                                              __nv_bfloat16* __restrict__ out,
+                                                              float* __restrict__ partials, int rows, int dim,
+                                                              DropoutCfg drop, uint32_t stream) {
+  float ps[GPT][8];
+#pragma unroll
+  for (int i = 0; i < GPT; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ps[i][e] = 0.f;
+  const int groups = dim >> 3;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+#pragma unroll
+    for (int i = 0; i < GPT; ++i) {
+      const int gcol = i * 288 + threadIdx.x;
+      if (gcol < groups) {
+        const size_t gidx = (size_t)row * groups + gcol;
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(in) + 2 * gidx);
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(in) + 2 * gidx + 1);
+        float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        if (drop.thr != 0) {
+          const uint4 bits = dropout_bits8(drop, stream, (uint64_t)gidx);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            f[e] = dropout_keep(bits, e, drop.thr) ? bf16_round(bf16_round(f[e]) * drop.scale) : 0.0f;
+        }
+        uint4 o;
+        o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+        o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+        reinterpret_cast<uint4*>(out)[gidx] = o;
+        ps[i][0] += bf16_lo(o.x); ps[i][1] += bf16_hi(o.x); ps[i][2] += bf16_lo(o.y); ps[i][3] += bf16_hi(o.y);
+        ps[i][4] += bf16_lo(o.z); ps[i][5] += bf16_hi(o.z); ps[i][6] += bf16_lo(o.w); ps[i][7] += bf16_hi(o.w);
+      }
+    }
+  }
+  float* pr = partials + (size_t)blockIdx.x * dim;
+#pragma unroll
+  for (int i = 0; i < GPT; ++i) {
+    const int gcol = i * 288 + threadIdx.x;
+    if (gcol < groups) {
+      *reinterpret_cast<float4*>(pr + 8 * gcol) = make_float4(ps[i][0], ps[i][1], ps[i][2], ps[i][3]);
+      *reinterpret_cast<float4*>(pr + 8 * gcol + 4) = make_float4(ps[i][4], ps[i][5], ps[i][6], ps[i][7]);
+    }
+  }
+}
+
+// One launch that finishes any number of partial column-sum sets:
+//   out[c] = sum_{j < chunks} partials[j * chunk_stride + c],  fixed order (deterministic).
+struct FinalizeTasks {
+  b200b_colsum_task t[B200B_MAX_COLSUM_TASKS];
+  int n;
+};
+// Block = 32 columns x 16 chunk-lanes: lane ty sums chunks ty, ty+16, ... (4 loads in flight), then
+// the 16 lanes are combined through shared memory in a fixed order.
+__global__ void __launch_bounds__(512) colsum_finalize_multi_kernel(const FinalizeTasks tasks) {
+  const b200b_colsum_task& t = tasks.t[blockIdx.y];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  if (blockIdx.x * 32 >= t.cols) return;  // whole block out of range for this (shorter) task
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < t.cols) {
+    int j = ty;
+    for (; j + 48 < t.chunks; j += 64) {
+      s0 += t.partials[(size_t)j * t.chunk_stride + c];
+      s1 += t.partials[(size_t)(j + 16) * t.chunk_stride + c];
+      s2 += t.partials[(size_t)(j + 32) * t.chunk_stride + c];
+      s3 += t.partials[(size_t)(j + 48) * t.chunk_stride + c];
+    }
+    for (; j < t.chunks; j += 16) s0 += t.partials[(size_t)j * t.chunk_stride + c];
+  }
+  __shared__ float sh[16][33];
+  sh[ty][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ty == 0 && c < t.cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += sh[k][tx];
+    t.out[c] = s;
+  }
+}
+
 template <typename K, typename... Args>
 static int launch_rows(K kern, int rows, cudaStream_t stream, const char* what, Args... args) {
   const int warps = 8;
@@ -368,4 +645,165 @@ extern "C" int b200b_cast_bf16(const float* in, void* out_bf16, int64_t n, float
   cast_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out_bf16), n8,
                                                     make_dropout_cfg(dropout_p, seed), dropout_stream);
   return check_launch("cast_bf16", stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-per-row entry points
+// ------------------------------------------------------------------------------------------------
+#define B200B_DISPATCH_VPT(dim, CALL)                                        \
+  do {                                                                       \
+    const int v_ = ((dim) / 4 + kRowThreads - 1) / kRowThreads;              \
+    if (v_ <= 1) { CALL(1); }                                                \
+    else if (v_ <= 2) { CALL(2); }                                           \
+    else if (v_ <= 3) { CALL(3); }                                           \
+    else if (v_ <= 6) { CALL(6); }                                           \
+    else {                                                                   \
+      set_last_error("row kernels: dim %d > 4608 not supported", (dim));     \
+      return B200B_ERR_SHAPE;                                                \
+    }                                                                        \
+  } while (0)
+
+extern "C" int b200b_row_chunks(int rows) {
+  int num_sms = 0;
+  if (device_sm_count(&num_sms) != B200B_OK) return 0;
+  const int cap = 2 * num_sms;
+  return rows < cap ? (rows > 0 ? rows : 0) : cap;
+}
+
+extern "C" int b200b_layernorm_fwd_rows(const float* x, const float* gamma, const float* beta, void* y_bf16,
+                                        float* mean, float* rstd, int rows, int dim, float eps, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !gamma || !beta || !y_bf16 || !mean || !rstd) {
+    set_last_error("layernorm_fwd_rows: null argument");
+    return B200B_ERR_ARG;
+  }
+  if (rows <= 0 || dim <= 0 || (dim % 4) != 0) {
+    set_last_error("layernorm_fwd_rows: need rows > 0 and dim %% 4 == 0 (rows=%d dim=%d)", rows, dim);
+    return B200B_ERR_SHAPE;
+  }
+  if (!al16(x) || !al16(gamma) || !al16(beta) || (reinterpret_cast<uintptr_t>(y_bf16) & 7)) {
+    set_last_error("layernorm_fwd_rows: misaligned pointer");
+    return B200B_ERR_ALIGN;
+  }
+  int num_sms = 0;
+  int rc = device_sm_count(&num_sms);
+  if (rc != B200B_OK) return rc;
+  const int grid = rows < 8 * num_sms ? rows : 8 * num_sms;
+#define CALL(V)                                                                                                   \
+  layernorm_fwd_row_kernel<V><<<grid, kRowThreads, 0, stream>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), \
+                                                                mean, rstd, rows, dim, eps)
+  B200B_DISPATCH_VPT(dim, CALL);
+#undef CALL
+  return check_launch("layernorm_fwd", stream);
+}
+
+extern "C" int b200b_layernorm_bwd_fused(const void* dy_bf16, const float* x, const float* mean, const float* rstd,
+                                         const float* gamma, const float* dres, float* dx, void* dy_next_bf16,
+                                         float* partials, int rows, int dim, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!dy_bf16 || !x || !mean || !rstd || !gamma || !partials) {
+    set_last_error("layernorm_bwd_fused: null argument");
+    return B200B_ERR_ARG;
+  }
+  if (dx == nullptr && dy_next_bf16 != nullptr) {
+    set_last_error("layernorm_bwd_fused: dy_next needs dx");
+    return B200B_ERR_ARG;
+  }
+  if (rows <= 0 || dim <= 0 || (dim % 4) != 0) {
+    set_last_error("layernorm_bwd_fused: need rows > 0 and dim %% 4 == 0 (rows=%d dim=%d)", rows, dim);
+    return B200B_ERR_SHAPE;
+  }
+  if (!al16(x) || !al16(gamma) || (dx && !al16(dx)) || (dres && !al16(dres)) || !al16(partials) ||
+      (reinterpret_cast<uintptr_t>(dy_bf16) & 7) || (reinterpret_cast<uintptr_t>(dy_next_bf16) & 7)) {
+    set_last_error("layernorm_bwd_fused: misaligned pointer");
+    return B200B_ERR_ALIGN;
+  }
+  const int grid = b200b_row_chunks(rows);
+  if (grid <= 0) return B200B_ERR_DEVICE;
+#define CALL(V)                                                                                              \
+  layernorm_bwd_row_kernel<V><<<grid, kRowThreads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16), x, mean, \
+                                                                rstd, gamma, dres, dx,                       \
+                                                                reinterpret_cast<__nv_bfloat16*>(dy_next_bf16), partials, rows, dim)
+  B200B_DISPATCH_VPT(dim, CALL);
+#undef CALL
+  return check_launch("layernorm_bwd", stream);
+}
+
+extern "C" int b200b_cast_bf16_colsum(const float* in, void* out_bf16, float* partials, int rows, int dim,
+                                      float dropout_p, uint64_t seed, uint32_t dropout_stream, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!in || !out_bf16 || !partials) {
+    set_last_error("cast_bf16_colsum: null argument");
+    return B200B_ERR_ARG;
+  }
+  if (rows <= 0 || dim <= 0 || (dim % 8) != 0 || dim > 8 * 288 * 4) {
+    set_last_error("cast_bf16_colsum: need rows > 0, dim %% 8 == 0, dim <= 9216 (rows=%d dim=%d)", rows, dim);
+    return B200B_ERR_SHAPE;
+  }
+  if (!al16(in) || !al16(out_bf16) || !al16(partials)) {
+    set_last_error("cast_bf16_colsum: misaligned pointer");
+    return B200B_ERR_ALIGN;
+  }
+  if (!(dropout_p >= 0.0f && dropout_p < 1.0f)) {
+    set_last_error("cast_bf16_colsum: dropout_p must be in [0,1)");
+    return B200B_ERR_ARG;
+  }
+  const int grid = b200b_row_chunks(rows);
+  if (grid <= 0) return B200B_ERR_DEVICE;
+  const DropoutCfg dc = make_dropout_cfg(dropout_p, seed);
+  const int gpt = (dim / 8 + 287) / 288;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  if (gpt <= 1) cast_colsum_row_kernel<1><<<grid, 288, 0, stream>>>(in, o, partials, rows, dim, dc, dropout_stream);
+  else if (gpt <= 2) cast_colsum_row_kernel<2><<<grid, 288, 0, stream>>>(in, o, partials, rows, dim, dc, dropout_stream);
+  else cast_colsum_row_kernel<4><<<grid, 288, 0, stream>>>(in, o, partials, rows, dim, dc, dropout_stream);
+  return check_launch("cast_colsum", stream);
+}
+
+extern "C" int b200b_colsum_partials(const void* dy_bf16, int64_t ld, int rows, int cols, float* partials,
+                                     int* chunks_out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!dy_bf16 || !partials || !chunks_out) {
+    set_last_error("colsum_partials: null argument");
+    return B200B_ERR_ARG;
+  }
+  if (rows <= 0 || cols <= 0 || (cols % 4) != 0 || (ld % 4) != 0) {
+    set_last_error("colsum_partials: need rows > 0, cols %% 4 == 0, ld %% 4 == 0");
+    return B200B_ERR_SHAPE;
+  }
+  if ((reinterpret_cast<uintptr_t>(dy_bf16) & 7) || !al16(partials)) {
+    set_last_error("colsum_partials: misaligned pointer");
+    return B200B_ERR_ALIGN;
+  }
+  int num_sms = 0;
+  int rc = device_sm_count(&num_sms);
+  if (rc != B200B_OK) return rc;
+  const int chunks = colsum_chunks(rows, cols, num_sms);
+  const int rows_per_chunk = (rows + chunks - 1) / chunks;
+  dim3 grid((cols + 127) / 128, chunks);
+  colsum_partial_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16), (long long)ld, nullptr,
+                                                  nullptr, nullptr, partials, nullptr, rows, cols, rows_per_chunk);
+  *chunks_out = chunks;
+  return check_launch("colsum_partial", stream);
+}
+
+extern "C" int b200b_colsum_finalize(const b200b_colsum_task* tasks, int ntasks, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!tasks || ntasks <= 0 || ntasks > B200B_MAX_COLSUM_TASKS) {
+    set_last_error("colsum_finalize: need 1..%d tasks", B200B_MAX_COLSUM_TASKS);
+    return B200B_ERR_ARG;
+  }
+  FinalizeTasks ft;
+  ft.n = ntasks;
+  int max_cols = 0;
+  for (int i = 0; i < ntasks; ++i) {
+    if (!tasks[i].partials || !tasks[i].out || tasks[i].cols <= 0 || tasks[i].chunks <= 0) {
+      set_last_error("colsum_finalize: bad task %d", i);
+      return B200B_ERR_ARG;
+    }
+    ft.t[i] = tasks[i];
+    if (tasks[i].cols > max_cols) max_cols = tasks[i].cols;
+  }
+  dim3 grid((max_cols + 31) / 32, ntasks);
+  colsum_finalize_multi_kernel<<<grid, 512, 0, stream>>>(ft);
+  return check_launch("colsum_final", stream);
 }

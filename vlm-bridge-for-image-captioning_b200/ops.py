@@ -92,6 +92,71 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: t
     return out
 
 
+def layernorm_fwd_rows(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5):
+    """CTA-per-row LayerNorm forward: x f32 [rows, dim] -> (y bf16, mean, rstd)."""
+    _need_cuda(x, gamma, beta)
+    rows, dim = x.shape
+    y = torch.empty((rows, dim), device=x.device, dtype=torch.bfloat16)
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200b_layernorm_fwd_rows(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                                   mean.data_ptr(), rstd.data_ptr(), rows, dim, eps, _stream_ptr()),
+               "layernorm_fwd_rows")
+    return y, mean, rstd
+
+
+def finalize_colsums(tasks) -> None:
+    """tasks: [(partials tensor (any view), out f32 [cols], cols, chunks, chunk_stride)] -> one launch."""
+    arr = (_lib.ColsumTask * len(tasks))()
+    for i, (part, out, cols, chunks, stride) in enumerate(tasks):
+        arr[i] = _lib.ColsumTask(part.data_ptr(), out.data_ptr(), cols, chunks, stride)
+    _lib.check(_lib.lib().b200b_colsum_finalize(arr, len(tasks), _stream_ptr()), "colsum_finalize")
+
+
+def layernorm_bwd_fused(dy, x, mean, rstd, gamma, dres=None, want_dx=True, want_dy_next=True):
+    """Fused LN backward: returns (dx f32 | None, dy_next bf16 | None, dbeta, dgamma, colsum(dy_next) | None)."""
+    _need_cuda(dy, x, mean, rstd, gamma, dres)
+    rows, dim = x.shape
+    chunks = _lib.lib().b200b_row_chunks(rows)
+    part = torch.empty((chunks, 3, dim), device=x.device, dtype=torch.float32)
+    dx = torch.empty_like(x) if want_dx else None
+    dyn = torch.empty((rows, dim), device=x.device, dtype=torch.bfloat16) if (want_dx and want_dy_next) else None
+    _lib.check(_lib.lib().b200b_layernorm_bwd_fused(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                    gamma.data_ptr(), _ptr(dres), _ptr(dx), _ptr(dyn), part.data_ptr(),
+                                                    rows, dim, _stream_ptr()), "layernorm_bwd_fused")
+    outs = [torch.empty(dim, device=x.device, dtype=torch.float32) for _ in range(3)]
+    n_out = 3 if dyn is not None else 2
+    finalize_colsums([(part[0, j], outs[j], dim, chunks, 3 * dim) for j in range(n_out)])
+    return dx, dyn, outs[0], outs[1], (outs[2] if dyn is not None else None)
+
+
+def cast_bf16_colsum(x: torch.Tensor, dropout_p: float = 0.0, seed: int = 0, dropout_stream: int = 0):
+    """x f32 [rows, dim] -> (bf16 copy with the dropout-backward mask, its column sums f32 [dim])."""
+    _need_cuda(x)
+    rows, dim = x.shape
+    chunks = _lib.lib().b200b_row_chunks(rows)
+    part = torch.empty((chunks, dim), device=x.device, dtype=torch.float32)
+    out = torch.empty((rows, dim), device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().b200b_cast_bf16_colsum(x.data_ptr(), out.data_ptr(), part.data_ptr(), rows, dim, dropout_p,
+                                                 seed, dropout_stream, _stream_ptr()), "cast_bf16_colsum")
+    s = torch.empty(dim, device=x.device, dtype=torch.float32)
+    finalize_colsums([(part, s, dim, chunks, dim)])
+    return out, s
+
+
+def colsum_two_stage(dy: torch.Tensor) -> torch.Tensor:
+    """b200b_colsum_partials + b200b_colsum_finalize (the path the block backward uses)."""
+    _need_cuda(dy)
+    rows, cols = dy.shape
+    part = torch.empty((64, cols), device=dy.device, dtype=torch.float32)
+    ch = C.c_int(0)
+    _lib.check(_lib.lib().b200b_colsum_partials(dy.data_ptr(), dy.stride(0), rows, cols, part.data_ptr(), C.byref(ch),
+                                                _stream_ptr()), "colsum_partials")
+    s = torch.empty(cols, device=dy.device, dtype=torch.float32)
+    finalize_colsums([(part, s, cols, ch.value, cols)])
+    return s
+
+
 def colsum(dy: torch.Tensor, *, x: torch.Tensor | None = None, mean: torch.Tensor | None = None,
            rstd: torch.Tensor | None = None, out_sum: torch.Tensor | None = None,
            out_gsum: torch.Tensor | None = None, workspace: torch.Tensor | None = None):
