@@ -221,7 +221,9 @@ def run_b200_arm(args) -> int:
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a collective that a rank never joins aborts after 2 minutes instead of hanging the box
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
 
     from vlm_bridge_b200 import BridgeLite, VisionKVCache, _lib
     from vlm_bridge_b200.parallel import broadcast_parameters, enable_data_parallel
@@ -239,7 +241,8 @@ def run_b200_arm(args) -> int:
         with torch.no_grad():
             model(vision_d, text_d)  # flattens parameters
         broadcast_parameters(model)
-        enable_data_parallel(model)
+        enable_data_parallel(model, grad_dtype=torch.float32 if args.grad_dtype == "f32" else torch.bfloat16,
+                             backend=args.dp_backend, nvls_blocks=args.nvls_blocks, nvls_threads=args.nvls_threads, bucket_bytes=args.bucket_mb << 20)
 
     def step(v, t):
         model._w16_key = None            # weights count as updated by the optimizer since last step
@@ -249,6 +252,24 @@ def run_b200_arm(args) -> int:
         loss = y.float().square().mean()
         loss.backward()
         return loss
+
+    # The timed loops replay one captured CUDA graph of exactly this step (GraphedBridgeStep: forward,
+    # loss, backward, weight re-cast, gradient exchange) unless --no-graph; the eager `step` remains for
+    # the per-kernel event pass. Same kernels, same work; only the host-side enqueue cost differs.
+    graphed, graph_error = None, None
+    if not args.no_graph:
+        from vlm_bridge_b200 import GraphedBridgeStep
+        try:
+            graphed = GraphedBridgeStep(model, lambda y: y.float().square().mean(), vision_d, text_d)
+        except Exception as e:  # noqa: BLE001
+            graph_error = repr(e)[:200]
+            graphed = None
+            torch.cuda.synchronize()
+
+    def run_step(v, t):
+        if graphed is None:
+            return step(v, t)
+        return graphed.replay() if v is vision_d else graphed(v, t)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -260,22 +281,28 @@ def run_b200_arm(args) -> int:
     if rank == 0:
         sampler.start()
     for _ in range(max(3, args.warmup)):
-        step(vision_d, text_d)
+        run_step(vision_d, text_d)
     # ---- timed region: device-resident inputs -------------------------------------------------
     sync_all()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.mark(True)
     e0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
-        step(vision_d, text_d)
+        run_step(vision_d, text_d)
+    host_ms_step = (time.perf_counter() - t_host0) * 1e3 / args.steps   # time to ENQUEUE a step (no sync inside)
     e1.record()
     sync_all()
     sampler.mark(False)
     launches = _lib.launch_count() - launches0
+    if graphed is not None:
+        launches = graphed.kernels_per_replay * args.steps   # replayed launches are not seen by the host counter
     ms_total = e0.elapsed_time(e1)
     # ---- end-to-end: host buffers in, loss out, through the public nn.Module API ---------------
     def e2e_step():
+        if graphed is not None:          # pinned host -> the graph's input buffers -> replay -> loss to host
+            return float(graphed(vision_h, text_h).item())
         v = vision_h.to(dev, non_blocking=True)
         t = text_h.to(dev, non_blocking=True)
         return float(step(v, t).item())
@@ -308,18 +335,66 @@ def run_b200_arm(args) -> int:
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": vision_h.numel() * 4 + text_h.numel() * 4, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
+        "host_enqueue_ms_per_step": host_ms_step,
+        "launch_mode": ("cuda graph replay (GraphedBridgeStep)" if graphed is not None
+                        else "eager" + (f" (graph capture failed: {graph_error})" if graph_error else "")),
         "clocks": clocks,
     }
 
+    if world > 1:
+        # the same steps with the gradient exchange switched off: what the all-reduce costs per step
+        from vlm_bridge_b200.parallel import disable_data_parallel
+        reducer = model._bucket_hook
+        disable_data_parallel(model)
+        sync_all()
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        graphed_dp, graphed = graphed, None
+        if graphed_dp is not None:
+            try:
+                graphed = GraphedBridgeStep(model, lambda y: y.float().square().mean(), vision_d, text_d)
+            except Exception:  # noqa: BLE001
+                graphed = None
+        for _ in range(3):
+            run_step(vision_d, text_d)
+        sync_all()
+        e4.record()
+        t_host0 = time.perf_counter()
+        for _ in range(args.steps):
+            run_step(vision_d, text_d)
+        host_ms_nodp = (time.perf_counter() - t_host0) * 1e3 / args.steps
+        e5.record()
+        sync_all()
+        t_local = torch.tensor([e4.elapsed_time(e5)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+        model._bucket_hook = reducer
+        graphed = graphed_dp
+        trace = None
+        if reducer.backend == "nvls":
+            reducer.trace = []
+            step(vision_d, text_d)
+            bwd_end = torch.cuda.Event(enable_timing=True)
+            bwd_end.record()
+            torch.cuda.synchronize()
+            trace = {"buckets": reducer.trace_report(), "backward_end_ms": round(reducer._t0.elapsed_time(bwd_end), 3)}
+            reducer.trace = None
+            sync_all()
+        line["dp"] = {"trace": trace,"allreduce": reducer.describe(), "bytes_per_step": reducer.bytes_per_step,
+                      "ms_per_step_without_allreduce": float(t_local[0]) / args.steps,
+                      "host_enqueue_ms_per_step_without_allreduce": host_ms_nodp,
+                      "exposed_allreduce_ms": ms_step - float(t_local[0]) / args.steps}
+
+    # ---- per-kernel timing pass (CUDA events on the launching stream, outside the timed region);
+    # every rank runs the steps (they contain the gradient all-reduce), rank 0 records ----
+    prof_steps = min(args.steps, 10)
+    sync_all()
+    if rank == 0:
+        _lib.profile_begin(torch.cuda.current_stream().cuda_stream)
+    for _ in range(prof_steps):
+        step(vision_d, text_d)
+    entries = _lib.profile_end() if rank == 0 else []
+    sync_all()
     if rank == 0:
         peaks = load_peaks()
-        # ---- per-kernel timing pass (CUDA events on the launching stream, outside the timed region) ----
-        prof_steps = min(args.steps, 10)
-        torch.cuda.synchronize()
-        _lib.profile_begin(torch.cuda.current_stream().cuda_stream)
-        for _ in range(prof_steps):
-            step(vision_d, text_d)
-        entries = _lib.profile_end()
         by_kernel: dict[str, list[float]] = {}
         for name, ms in entries:
             by_kernel.setdefault(name, []).append(ms)
@@ -427,6 +502,14 @@ def main() -> int:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
+    ap.add_argument("--dp-backend", default="auto", choices=["auto", "nvls", "nccl"],
+                    help="transport of the gradient exchange: own NVLS multimem kernel, or NCCL")
+    ap.add_argument("--nvls-blocks", type=int, default=148)
+    ap.add_argument("--nvls-threads", type=int, default=128)
+    ap.add_argument("--bucket-mb", type=int, default=32)
+    ap.add_argument("--grad-dtype", default="bf16", choices=["bf16", "f32"],
+                    help="dtype of the data-parallel weight-gradient exchange (N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

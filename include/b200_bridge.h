@@ -213,8 +213,20 @@ typedef struct b200b_bridge_dims {
   int32_t dim, dim_vision, dim_ffn;
   int32_t heads_cross, heads_self;
   int32_t num_blocks;
-  int32_t reserved;
+  int32_t flags;        /* B200B_BRIDGE_* bits, 0 = defaults */
 } b200b_bridge_dims;
+
+/* flags: the 2-D weight gradients (b200b_block_grads.wq_c .. w2, dwkv_all) are written as bf16 --
+ * the rounding autocast applies to them in the reference (the gradient of a bf16-cast weight is a
+ * bf16 tensor) -- instead of fp32. Used by the data-parallel path, which exchanges them in bf16. */
+#define B200B_BRIDGE_WGRAD_BF16 1
+/* flags: the `seed` argument of block_forward / block_backward is a device pointer to a uint64 seed
+ * that every dropout kernel reads when it runs, so that a captured CUDA graph draws fresh masks on
+ * every replay (the caller advances the value between replays, e.g. with a captured add kernel). */
+#define B200B_BRIDGE_SEED_INDIRECT 2
+/* The same for the individual operators: OR this bit into `dropout_stream` and pass the device
+ * pointer (cast to uint64_t) as `seed`. */
+#define B200B_SEED_INDIRECT 0x80000000u
 
 typedef struct b200b_block_weights {
   const void* wq_c;   /* bf16 [D, D]    cross_attention.w_q.weight                         */
@@ -234,9 +246,10 @@ typedef struct b200b_block_weights {
   const float* ln_f_g; const float* ln_f_b; /* ln_ffn    */
 } b200b_block_weights;
 
-/* fp32 gradient destinations of one block, same shapes as the weights above */
+/* gradient destinations of one block, same shapes as the weights above; the six matrices are
+ * fp32, or bf16 under B200B_BRIDGE_WGRAD_BF16; vectors are always fp32 */
 typedef struct b200b_block_grads {
-  float* wq_c; float* wo_c; float* wqkv_s; float* wo_s; float* w1; float* w2;
+  void* wq_c; void* wo_c; void* wqkv_s; void* wo_s; void* w1; void* w2;
   float* bq_c; float* bo_c; float* bqkv_s; float* bo_s; float* b1; float* b2;
   float* ln_c_g; float* ln_c_b; float* ln_s_g; float* ln_s_b; float* ln_f_g; float* ln_f_b;
 } b200b_block_grads;
@@ -261,18 +274,68 @@ int b200b_bridge_block_forward(const b200b_bridge_dims* dims, int block_index,
                                float* x_out, void* saved, size_t saved_bytes, float dropout_p,
                                uint64_t seed, void* stream);
 
+/* Optional host callback of the backward entry points: fn(user, grad, elems) is called on the
+ * calling thread right after the kernel that produces the weight-gradient matrix `grad` (`elems`
+ * elements) has been enqueued, in the order backward finishes them (w2, w1, wo_s, wqkv_s, wo_c,
+ * wq_c). The data-parallel reducer uses it to start a bucket's exchange while the rest of the
+ * block's backward is still running. */
+typedef void (*b200b_grad_ready_fn)(void* user, const void* grad, int64_t elems);
+typedef struct b200b_grad_notify {
+  b200b_grad_ready_fn fn;
+  void* user;
+} b200b_grad_notify;
+
 /* Backward of one block. d_out f32 [T, D] is the gradient of x_out; writes every field of `g`,
- * the block's columns of dkv bf16 [Tv, nb*2D], and (if d_in != NULL) d_in f32 [T, D]. */
+ * the block's columns of dkv bf16 [Tv, nb*2D], and (if d_in != NULL) d_in f32 [T, D].
+ * notify may be NULL. */
 int b200b_bridge_block_backward(const b200b_bridge_dims* dims, int block_index,
                                 const b200b_block_weights* w, const float* x_in, const void* kv,
                                 const void* saved, const float* d_out, float* d_in, void* dkv,
                                 const b200b_block_grads* g, void* workspace, size_t workspace_bytes,
-                                float dropout_p, uint64_t seed, void* stream);
+                                float dropout_p, uint64_t seed, const b200b_grad_notify* notify,
+                                void* stream);
 
-/* dwkv_all f32 [nb*2D, Dv] = dkv^T @ vision_bf16 ; dbkv_all f32 [nb*2D] = column sums of dkv */
+/* dwkv_all [nb*2D, Dv] (f32, or bf16 under B200B_BRIDGE_WGRAD_BF16) = dkv^T @ vision_bf16 ;
+ * dbkv_all f32 [nb*2D] = column sums of dkv */
 int b200b_bridge_kv_backward(const b200b_bridge_dims* dims, const void* vision_bf16,
-                             const void* dkv, float* dwkv_all, float* dbkv_all, void* workspace,
+                             const void* dkv, void* dwkv_all, float* dbkv_all, void* workspace,
                              size_t workspace_bytes, void* stream);
+
+/* out f32 [n] = scale * in bf16 [n] (n % 8 == 0): turns an exchanged bf16 gradient bucket into
+ * the fp32 .grad the optimizer reads. */
+int b200b_bf16_to_f32(const void* in_bf16, float* out, int64_t n, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
+ * Data-parallel gradient exchange over NVLink / NVSwitch (csrc/allreduce_nvls.cu). The reference has
+ * no distributed code; this is the exchange step of SURVEY.md 8e.
+ *
+ * The caller owns a SYMMETRIC buffer (same size on every rank, every rank's copy mapped in this
+ * process, plus one multicast address that targets all copies -- e.g. obtained from
+ * torch.distributed._symmetric_memory) and a symmetric, zero-initialised flag array of
+ * b200b_allreduce_nvls_flag_bytes() bytes per rank. b200b_allreduce_nvls averages (scale = 1/world)
+ * or sums (scale = 1) bytes [byte_offset, byte_offset + bytes) of the buffer over all ranks, in
+ * place, with multimem.ld_reduce / multimem.st; with out_f32 != NULL (bf16 only) it also writes the
+ * reduced slice as fp32 to out_f32[0 .. bytes/2). Every rank must call it with the same arguments
+ * (`blocks` CTAs of `threads` threads included) and the same, strictly increasing collective number,
+ * one call at a time per communicator. The collective number is `epoch` (1, 2, 3, ...), or, with
+ * epoch_base != NULL, `epoch + *epoch_base` read on the device when the kernel runs: a captured CUDA
+ * graph then numbers its collectives 1..n and advances *epoch_base by n once per replay.
+ * A rank that never arrives makes the others trap after ~10 s instead of hanging.
+ * ------------------------------------------------------------------------------------------- */
+#define B200B_NVLS_MAX_RANKS 8
+#define B200B_NVLS_MAX_BLOCKS 160
+#define B200B_DTYPE_BF16 0
+#define B200B_DTYPE_F32 1
+typedef struct b200b_nvls_comm {
+  void* multicast_base;                 /* multicast address of byte 0 of the symmetric buffer */
+  void* local_base;                     /* this rank's own copy */
+  void* flags[B200B_NVLS_MAX_RANKS];    /* flag array of rank q as mapped in this process */
+  int32_t rank, world;
+} b200b_nvls_comm;
+size_t b200b_allreduce_nvls_flag_bytes(void);
+int b200b_allreduce_nvls(const b200b_nvls_comm* comm, int dtype, int64_t byte_offset, int64_t bytes,
+                         float scale, float* out_f32, uint32_t epoch, const uint32_t* epoch_base,
+                         int blocks, int threads, void* stream);
 
 #ifdef __cplusplus
 }

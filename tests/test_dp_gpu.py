@@ -1,0 +1,90 @@
+"""Data-parallel gradient exchange on real GPUs (needs >= 2 devices; skipped otherwise).
+
+Each rank runs fwd+bwd on its own batch shard with the reducer attached; the averaged gradients it
+ends with must equal the average of the per-shard gradients computed without any exchange
+(fp32 exchange: to reduction-order tolerance; bf16 exchange: to bf16 rounding of the buckets)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    import datetime
+
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev,
+                            timeout=datetime.timedelta(seconds=90))
+    from vlm_bridge_b200 import BridgeLite
+    from vlm_bridge_b200.parallel import broadcast_parameters, disable_data_parallel, enable_data_parallel
+
+    torch.manual_seed(0)
+    m = BridgeLite(dropout=0.0).to(dev).train()
+
+    def shard(r):
+        g = torch.Generator().manual_seed(1234 + r)
+        return torch.randn(2, 33, 1024, generator=g).to(dev), torch.randn(2, 24, 2304, generator=g).to(dev)
+
+    def grads(v, t):
+        for p in m.parameters():
+            p.grad = None
+        m(v, t).float().square().mean().backward()
+        return torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone()
+
+    with torch.no_grad():
+        m(*shard(rank))                        # flattens the parameters
+    broadcast_parameters(m)
+    want = torch.stack([grads(*shard(r)) for r in range(world)]).mean(0)      # no exchange
+    res = {}
+    for name, backend, dtype, tol in (("f32", "nccl", torch.float32, 1e-5), ("bf16", "nccl", torch.bfloat16, 1.5e-2),
+                                      ("nvls_f32", "nvls", torch.float32, 1e-5),
+                                      ("nvls_bf16", "nvls", torch.bfloat16, 1.5e-2)):
+        red = enable_data_parallel(m, bucket_bytes=8 << 20, grad_dtype=dtype, backend=backend)
+        got = grads(*shard(rank))
+        torch.cuda.synchronize()
+        err = float((got - want).norm() / want.norm())
+        res[name] = (err, tol, red.buckets_per_step, red.bytes_per_step)
+        got2 = grads(*shard(rank))             # a second step reuses the symmetric buffers and flags
+        torch.cuda.synchronize()
+        res[name + "_again"] = (float((got2 - want).norm() / want.norm()), tol, red.buckets_per_step, red.bytes_per_step)
+        disable_data_parallel(m)
+    out[rank] = res
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_dp_gradients_match_average_of_shards():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        res = dict(out)
+    assert set(res) == {0, 1}
+    for rank, r in res.items():
+        for name, (err, tol, buckets, nbytes) in r.items():
+            assert err <= tol, f"rank {rank} {name}: rel err {err} > {tol}"
+            assert buckets >= 5
+        assert r["bf16"][3] < 0.51 * r["f32"][3] + 4 * 200000
+        assert r["nvls_bf16"][3] < 0.51 * r["nvls_f32"][3] + 4 * 200000

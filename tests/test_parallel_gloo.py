@@ -27,21 +27,48 @@ def _worker(rank, world, port, out):
     from vlm_bridge_b200.parallel import GradBucketReducer, broadcast_parameters
 
     lay = _Layout(2, 64, 32, 256)
-    g = torch.Generator().manual_seed(100 + rank)
-    arena = torch.randn(lay.total, generator=g)
-    mine = arena.clone()
-    red = GradBucketReducer(max_bucket_elems=5000)      # forces several chunks per slab
-    for s, e in lay.buckets():                          # the order BridgeLite._run_backward fires them
-        red(arena, s, e)
-    red.finish()
-    others = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(others, mine)
-    want = torch.stack(others).mean(0)
+    ok = True
+    for dtype in (torch.float32, torch.bfloat16):
+        g = torch.Generator().manual_seed(100 + rank)
+        mine = torch.randn(lay.total, generator=g)
+        if dtype == torch.bfloat16:                      # weight gradients are produced in bf16 in this mode
+            mine[:lay.n_weights] = mine[:lay.n_weights].bfloat16().float()
+        arena32 = mine.clone()
+        arena16 = mine[:lay.n_weights].bfloat16() if dtype == torch.bfloat16 else None
+        if arena16 is not None:
+            arena32[:lay.n_weights] = float("nan")       # must be filled by the reducer's conversion
+        red = GradBucketReducer(bucket_bytes=8000, grad_dtype=dtype)   # forces several buckets per slab
+        red.begin(arena32, arena16, lay.n_weights)
+        # the order BridgeLite._run_backward announces ranges: per block (last first) the six weight
+        # matrices from the end of the slab to its start, then the block's vector slab; K/V last
+        for i in reversed(range(lay.nb)):
+            pre = f"bridge_blocks.{i}."
+            names = ["ffn.3.weight", "ffn.0.weight", "self_attention.w_o.weight", "self_attention.w_q.weight",
+                     "cross_attention.w_o.weight", "cross_attention.w_q.weight"]
+            sizes = {"self_attention.w_q.weight": 3 * 64 * 64}
+            for n in names:
+                o = lay.offsets[pre + n]
+                e = o + sizes.get(n, {"ffn.3.weight": 64 * 256, "ffn.0.weight": 256 * 64}.get(n, 64 * 64))
+                red.weights_ready(o, e)
+            red.flush()
+            red.vectors_ready(lay.block_v_start[i], lay.block_v_end[i])
+        red.weights_ready(lay.kv_w_start, lay.block_w_start[0])
+        red.flush()
+        red.vectors_ready(lay.kv_b_start, lay.block_v_start[0])
+        red.finish()
+        others = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(others, mine)
+        want = torch.stack(others).mean(0)
+        tol = 1e-6 if dtype == torch.float32 else 2e-2   # bf16 sum of two bf16 values, then /2
+        ok = ok and torch.allclose(arena32, want, atol=tol, rtol=tol) and not torch.isnan(arena32).any()
+        esize = 4 if dtype == torch.float32 else 2
+        ok = ok and red.bytes_per_step == esize * lay.n_weights + 4 * (lay.total - lay.n_weights)
+        ok = ok and red.buckets_per_step > 4
     covered = torch.zeros(lay.total, dtype=torch.bool)
     for s, e in lay.buckets():
-        assert not covered[s:e].any()                   # buckets are disjoint
+        assert not covered[s:e].any()                   # slabs are disjoint
         covered[s:e] = True
-    ok = bool(covered.all()) and torch.allclose(arena, want, atol=1e-6) and red.bytes_reduced == 4 * lay.total
+    ok = ok and bool(covered.all())
     # broadcast_parameters: every rank ends with rank 0's tensors
     lin = torch.nn.Linear(8, 8)
     broadcast_parameters(lin)

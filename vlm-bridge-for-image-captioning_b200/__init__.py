@@ -6,4 +6,5 @@ __version__ = "0.1.0"
 
 from .bridge import (BridgeBlock, BridgeLite, MultiHeadCrossAttention,  # noqa: E402,F401
                      MultiHeadSelfAttention)
+from .graph import GraphedBridgeStep  # noqa: E402,F401
 from .kv_cache import VisionKVCache  # noqa: E402,F401

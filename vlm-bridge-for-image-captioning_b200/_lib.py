@@ -54,6 +54,11 @@ class ColsumTask(C.Structure):
                 ("chunk_stride", C.c_int64)]
 
 
+class NvlsComm(C.Structure):
+    _fields_ = [("multicast_base", C.c_void_p), ("local_base", C.c_void_p), ("flags", C.c_void_p * 8),
+                ("rank", C.c_int32), ("world", C.c_int32)]
+
+
 class AttnArgs(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("ldq", C.c_int64),
@@ -118,6 +123,13 @@ def _declare(lib) -> None:
     lib.b200b_colsum_partials.restype = C.c_int
     lib.b200b_colsum_partials.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int),
                                           C.c_void_p]
+    lib.b200b_bf16_to_f32.restype = C.c_int
+    lib.b200b_bf16_to_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
+    lib.b200b_allreduce_nvls_flag_bytes.restype = C.c_size_t
+    lib.b200b_allreduce_nvls_flag_bytes.argtypes = []
+    lib.b200b_allreduce_nvls.restype = C.c_int
+    lib.b200b_allreduce_nvls.argtypes = [C.POINTER(NvlsComm), C.c_int, C.c_int64, C.c_int64, C.c_float, C.c_void_p,
+                                         C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.b200b_colsum_finalize.restype = C.c_int
     lib.b200b_colsum_finalize.argtypes = [C.POINTER(ColsumTask), C.c_int, C.c_void_p]
     lib.b200b_attention_fwd.restype = C.c_int

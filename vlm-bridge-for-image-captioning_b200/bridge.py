@@ -176,7 +176,17 @@ class _Layout:
 
 class _BridgeDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("batch", "len_text", "len_vision", "dim", "dim_vision", "dim_ffn",
-                                         "heads_cross", "heads_self", "num_blocks", "reserved")]
+                                         "heads_cross", "heads_self", "num_blocks", "flags")]
+
+
+FLAG_WGRAD_BF16 = 1      # B200B_BRIDGE_WGRAD_BF16
+FLAG_SEED_INDIRECT = 2   # B200B_BRIDGE_SEED_INDIRECT
+_SEED_STRIDE = 0x1E3779B97F4A7C15  # odd 61-bit increment of the device-resident dropout seed
+_GRAD_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int64)
+
+
+class _GradNotify(C.Structure):
+    _fields_ = [("fn", _GRAD_READY_FN), ("user", C.c_void_p)]
 
 
 _W_FIELDS = ["wq_c", "wo_c", "wqkv_s", "wo_s", "w1", "w2", "bq_c", "bo_c", "bqkv_s", "bo_s", "b1", "b2",
@@ -210,7 +220,8 @@ def _declare_bridge(lib) -> None:
     lib.b200b_bridge_block_backward.restype = C.c_int
     lib.b200b_bridge_block_backward.argtypes = [P(_BridgeDims), C.c_int, P(_BlockPtrs), C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, P(_BlockPtrs),
-                                                C.c_void_p, C.c_size_t, C.c_float, C.c_uint64, C.c_void_p]
+                                                C.c_void_p, C.c_size_t, C.c_float, C.c_uint64, P(_GradNotify),
+                                                C.c_void_p]
     lib.b200b_bridge_kv_backward.restype = C.c_int
     lib.b200b_bridge_kv_backward.argtypes = [P(_BridgeDims), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_size_t, C.c_void_p]
@@ -272,8 +283,8 @@ class BridgeLite(nn.Module):
         self._w16: Optional[torch.Tensor] = None
         self._w16_key = None
         self._ptrs = None
-        # data-parallel hook: called as hook(grad_arena, start, end) when a bucket is final
-        self._bucket_hook: Optional[Callable[[torch.Tensor, int, int], None]] = None
+        # data-parallel reducer (parallel.GradBucketReducer) driven by _run_backward
+        self._bucket_hook = None
         self._last_grad_arena: Optional[torch.Tensor] = None
 
     # -- init exactly as the reference (bridge_module.py:394-404) ---------------------------------
@@ -289,7 +300,28 @@ class BridgeLite(nn.Module):
 
     # -- flat parameter storage --------------------------------------------------------------------
     def _named_params(self) -> list[tuple[str, nn.Parameter]]:
-        return list(self.named_parameters())
+        """(name, parameter) in registration order. Walking the module tree costs ~0.1 ms and a step
+        needs the list several times, so it is cached; the cache is checked against the owning
+        modules' `_parameters` dicts (one identity test per tensor), which catches a parameter that
+        was re-assigned, and dropped by `_apply` (.to / .cuda / .float)."""
+        cache = self.__dict__.get("_plist_cache")
+        if cache is not None:
+            for owner, key, _name, p in cache:
+                if owner._parameters.get(key) is not p:
+                    cache = None
+                    break
+        if cache is None:
+            cache = []
+            for mod_name, mod in self.named_modules():
+                for key, p in mod._parameters.items():
+                    if p is not None:
+                        cache.append((mod, key, (mod_name + "." if mod_name else "") + key, p))
+            self.__dict__["_plist_cache"] = cache
+        return [(name, p) for _, _, name, p in cache]
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__["_plist_cache"] = None
+        return super()._apply(fn, *args, **kwargs)
 
     def _ensure_flat(self) -> None:
         """Make every parameter a view of one flat fp32 CUDA buffer (re-done after .to()/.cuda())."""
@@ -321,27 +353,34 @@ class BridgeLite(nn.Module):
                 view.copy_(p.data)
                 p.data = view
         self._flat = flat
+        # device-resident dropout seed, used (and advanced by a captured kernel) under CUDA-graph capture
+        self._seed_dev = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).to(dev)
         self._w16 = torch.empty(lay.n_weights, device=dev, dtype=torch.bfloat16)
         self._w16_key = None
         self._ptrs = None
 
     def _refresh_bf16(self) -> None:
         key = tuple(p._version for _, p in self._named_params())
-        if key == self._w16_key:
+        # while a CUDA graph is being captured the cast is always recorded: the optimizer updates the
+        # fp32 masters between replays without this code running again
+        if key == self._w16_key and not torch.cuda.is_current_stream_capturing():
             return
         lay = self._layout
         _lib.check(_lib.lib().b200b_cast_bf16(self._flat.data_ptr(), self._w16.data_ptr(), lay.n_weights, 0.0, 0, 0,
                                               _stream()), "cast_bf16(weights)")
         self._w16_key = key
 
-    def _block_ptr_struct(self, base16: int, base32: int, i: int, grads: bool) -> _BlockPtrs:
+    def _block_ptr_struct(self, base16: int, base32: int, i: int, grads: bool, esize16: int = 2) -> _BlockPtrs:
+        """Pointers of block i's tensors: 2-D weights at base16 (a separate weight arena of
+        `esize16`-byte elements) when base16 is given, everything else at base32 (fp32 arena), both at
+        the flat-layout offsets."""
         lay = self._layout
         s = _BlockPtrs()
         pre = f"bridge_blocks.{i}."
         for field, key in zip(_W_FIELDS, _W_KEYS):
             off = lay.offsets[pre + key]
-            if off < lay.n_weights and not grads:
-                setattr(s, field, base16 + 2 * off)
+            if off < lay.n_weights and base16:
+                setattr(s, field, base16 + esize16 * off)
             else:
                 setattr(s, field, base32 + 4 * off)
         return s
@@ -352,10 +391,10 @@ class BridgeLite(nn.Module):
             self._ptrs = [self._block_ptr_struct(b16, b32, i, grads=False) for i in range(self.num_blocks)]
         return self._ptrs
 
-    def _dims(self, B: int, L: int, Nv: int) -> _BridgeDims:
+    def _dims(self, B: int, L: int, Nv: int, flags: int = 0) -> _BridgeDims:
         return _BridgeDims(batch=B, len_text=L, len_vision=Nv, dim=self.language_dim, dim_vision=self.vision_dim,
                            dim_ffn=self.language_dim * 4, heads_cross=self.num_heads_cross,
-                           heads_self=self.num_heads_self, num_blocks=self.num_blocks, reserved=0)
+                           heads_self=self.num_heads_self, num_blocks=self.num_blocks, flags=flags)
 
     # -- vision K/V (shared with the decode cache) -------------------------------------------------
     def project_vision_kv(self, vision_features: torch.Tensor):
@@ -404,7 +443,16 @@ class BridgeLite(nn.Module):
         n_arenas = self.num_blocks if keep_for_backward else 1
         saved = torch.empty(n_arenas * saved_bytes, device=dev, dtype=torch.uint8)
         p = self.dropout_p if self.training else 0.0
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
+        seed, flags = 0, 0
+        if p > 0:
+            if torch.cuda.is_current_stream_capturing():
+                # a host-drawn seed would be baked into the graph: keep it in device memory, advance it
+                # with a captured kernel, and let every dropout kernel read it when it runs
+                self._seed_dev.add_(_SEED_STRIDE)
+                seed, flags = self._seed_dev.data_ptr(), FLAG_SEED_INDIRECT
+                dims = self._dims(B, L, Nv, flags)
+            else:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         ptrs = self._weight_ptrs()
         xs = [x.view(B * L, D)]
         st = _stream()
@@ -421,6 +469,7 @@ class BridgeLite(nn.Module):
         state = None
         if keep_for_backward:
             state = dict(dims=dims, saved=saved, saved_bytes=saved_bytes, kv=kv, vb=vb, xs=xs[:-1], p=p, seed=seed,
+                         flags=flags,
                          versions=self._w16_key)
         return out, state
 
@@ -428,41 +477,72 @@ class BridgeLite(nn.Module):
         lay = self._layout
         dev = self._flat.device
         lib = _bridge_lib()
-        dims = state["dims"]
+        fdims = state["dims"]
         if state["versions"] != tuple(p._version for _, p in self._named_params()):
             raise RuntimeError("bridge parameters were modified in place between forward and backward")
-        B, L, D = dims.batch, dims.len_text, dims.dim
+        B, L, D = fdims.batch, fdims.len_text, fdims.dim
         d = d_out.detach().to(torch.float32).contiguous().view(B * L, D)
         garena = torch.empty(lay.total, device=dev, dtype=torch.float32)
         gbase = garena.data_ptr()
+        # data parallel: `reducer` exchanges gradient ranges as soon as their kernels are enqueued.
+        # With a bf16 exchange the weight-gradient GEMMs write a bf16 arena (the values autocast gives
+        # these gradients in the reference) and the reducer converts the averaged buckets into garena.
+        reducer = self._bucket_hook
+        g16 = None   # arena the weight-gradient GEMMs write when it is not garena itself
+        if reducer is not None and reducer.world_size > 1:
+            g16 = reducer.weight_arena(lay.n_weights, lay.total - lay.n_weights, dev)
+            if g16 is None and reducer.wgrad_bf16:
+                g16 = torch.empty(lay.n_weights, device=dev, dtype=torch.bfloat16)
+        wgrad_bf16 = g16 is not None and g16.dtype == torch.bfloat16
+        g16base = g16.data_ptr() if g16 is not None else 0
+        g16size = g16.element_size() if g16 is not None else 4
+        dims = self._dims(B, L, fdims.len_vision, (FLAG_WGRAD_BF16 if wgrad_bf16 else 0) | state["flags"])
         ws_bytes = lib.b200b_bridge_backward_workspace_bytes(C.byref(dims))
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         dkv = torch.empty_like(state["kv"])
         ptrs = self._weight_ptrs()
         st = _stream()
-        hook = self._bucket_hook
+        notify = None
+        if reducer is not None:
+            reducer.begin(garena, g16, lay.n_weights)
+            wbase, wsize = (g16base, g16size) if g16 is not None else (gbase, 4)
+
+            cb_errors: list[BaseException] = []
+
+            def _ready(_user, ptr, elems):
+                try:                                  # an exception cannot cross the C frame: keep it
+                    start = (ptr - wbase) // wsize
+                    reducer.weights_ready(start, start + elems)
+                except BaseException as e:  # noqa: BLE001
+                    cb_errors.append(e)
+
+            cb = _GRAD_READY_FN(_ready)            # kept alive until the end of this function
+            notify = _GradNotify(cb, None)
         for i in reversed(range(self.num_blocks)):
             need_din = i > 0 or text_needs_grad
             d_in = torch.empty((B * L, D), device=dev, dtype=torch.float32) if need_din else None
-            g = self._block_ptr_struct(0, gbase, i, grads=True)
+            g = self._block_ptr_struct(g16base, gbase, i, grads=True, esize16=g16size)
             arena = state["saved"].data_ptr() + i * state["saved_bytes"]
             _lib.check(lib.b200b_bridge_block_backward(
                 C.byref(dims), i, C.byref(ptrs[i]), state["xs"][i].data_ptr(), state["kv"].data_ptr(), arena,
                 d.data_ptr(), None if d_in is None else d_in.data_ptr(), dkv.data_ptr(), C.byref(g), ws.data_ptr(),
-                ws_bytes, state["p"], state["seed"], st), "block_backward")
-            if hook is not None:
-                hook(garena, lay.block_w_start[i], lay.block_w_end[i])
-                hook(garena, lay.block_v_start[i], lay.block_v_end[i])
+                ws_bytes, state["p"], state["seed"], None if notify is None else C.byref(notify), st),
+                "block_backward")
+            if reducer is not None:
+                if cb_errors:
+                    raise cb_errors[0]
+                reducer.flush()
+                reducer.vectors_ready(lay.block_v_start[i], lay.block_v_end[i])
             d = d_in
-        _lib.check(lib.b200b_bridge_kv_backward(C.byref(dims), state["vb"].data_ptr(), dkv.data_ptr(),
-                                                gbase + 4 * lay.kv_w_start, gbase + 4 * lay.kv_b_start, ws.data_ptr(),
-                                                ws_bytes, st), "kv_backward")
-        if hook is not None:
-            hook(garena, lay.kv_w_start, lay.block_w_start[0])
-            hook(garena, lay.kv_b_start, lay.block_v_start[0])
-            finish = getattr(hook, "finish", None)
-            if finish is not None:
-                finish()
+        _lib.check(lib.b200b_bridge_kv_backward(
+            C.byref(dims), state["vb"].data_ptr(), dkv.data_ptr(),
+            (g16base + g16size * lay.kv_w_start) if g16 is not None else (gbase + 4 * lay.kv_w_start),
+            gbase + 4 * lay.kv_b_start, ws.data_ptr(), ws_bytes, st), "kv_backward")
+        if reducer is not None:
+            reducer.weights_ready(lay.kv_w_start, lay.block_w_start[0])
+            reducer.flush()
+            reducer.vectors_ready(lay.kv_b_start, lay.block_v_start[0])
+            reducer.finish()
         self._last_grad_arena = garena
         grads = []
         for name, p in self._named_params():

@@ -29,6 +29,7 @@ struct ProfEvent {
 };
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
+static cudaStream_t g_prof_stream = nullptr;  // only launches on the profiled stream are timed
 static std::vector<ProfEvent> g_prof_events;
 
 int check_launch(const char* what, cudaStream_t stream) {
@@ -40,7 +41,7 @@ int check_launch(const char* what, cudaStream_t stream) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (g_prof_on) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
-    if (g_prof_on) {
+    if (g_prof_on && stream == g_prof_stream) {
       ProfEvent pe;
       pe.what = what;
       if (cudaEventCreate(&pe.ev) == cudaSuccess) {
@@ -97,7 +98,8 @@ extern "C" int b200b_profile_begin(void* stream_) {
     set_last_error("profile_begin: %s", cudaGetErrorString(e));
     return (int)e;
   }
-  cudaEventRecord(pe.ev, reinterpret_cast<cudaStream_t>(stream_));
+  g_prof_stream = reinterpret_cast<cudaStream_t>(stream_);
+  cudaEventRecord(pe.ev, g_prof_stream);
   g_prof_events.push_back(pe);
   g_prof_on = true;
   return B200B_OK;

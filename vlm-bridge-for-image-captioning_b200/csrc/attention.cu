@@ -160,6 +160,7 @@ __device__ __forceinline__ void store_rows_bf16(const float (&acc)[HD / 8][4], f
 // ================================================================================================
 template <int HD>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
+  const DropoutCfg drop = dropout_resolve(p.drop);
   using Cfg = AttnCfg<HD>;
   constexpr int BN = Cfg::kBN, kLd = Cfg::kLd;
   extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -248,17 +249,17 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
       o_acc[n][0] *= al0; o_acc[n][1] *= al0;
       o_acc[n][2] *= al1; o_acc[n][3] *= al1;
     }
-    if (p.drop.thr != 0) {
+    if (drop.thr != 0) {
       const uint64_t r0 = (bh * p.Lq + (uint64_t)(q0 + warp * 16 + g)) * (uint64_t)p.Lkp;
       const uint64_t r1 = r0 + (uint64_t)8 * p.Lkp;
 #pragma unroll
       for (int n = 0; n < BN / 8; ++n) {
-        const uint4 b0 = dropout_bits8(p.drop, p.drop_stream, (r0 + j0 + n * 8) >> 3);
-        const uint4 b1 = dropout_bits8(p.drop, p.drop_stream, (r1 + j0 + n * 8) >> 3);
-        s[n][0] = dropout_keep(b0, 2 * t4, p.drop.thr) ? s[n][0] * p.drop.scale : 0.f;
-        s[n][1] = dropout_keep(b0, 2 * t4 + 1, p.drop.thr) ? s[n][1] * p.drop.scale : 0.f;
-        s[n][2] = dropout_keep(b1, 2 * t4, p.drop.thr) ? s[n][2] * p.drop.scale : 0.f;
-        s[n][3] = dropout_keep(b1, 2 * t4 + 1, p.drop.thr) ? s[n][3] * p.drop.scale : 0.f;
+        const uint4 b0 = dropout_bits8(drop, p.drop_stream, (r0 + j0 + n * 8) >> 3);
+        const uint4 b1 = dropout_bits8(drop, p.drop_stream, (r1 + j0 + n * 8) >> 3);
+        s[n][0] = dropout_keep(b0, 2 * t4, drop.thr) ? s[n][0] * drop.scale : 0.f;
+        s[n][1] = dropout_keep(b0, 2 * t4 + 1, drop.thr) ? s[n][1] * drop.scale : 0.f;
+        s[n][2] = dropout_keep(b1, 2 * t4, drop.thr) ? s[n][2] * drop.scale : 0.f;
+        s[n][3] = dropout_keep(b1, 2 * t4 + 1, drop.thr) ? s[n][3] * drop.scale : 0.f;
       }
     }
     mma_frag_x_cols<HD, BN>(o_acc, s, Vs + (size_t)stage * BN * kLd, lane);
@@ -307,6 +308,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long
 // ================================================================================================
 template <int HD>
 __global__ void __launch_bounds__(128) attn_bwd_q_kernel(const AttnParams p) {
+  const DropoutCfg drop = dropout_resolve(p.drop);
   using Cfg = AttnCfg<HD>;
   constexpr int BN = Cfg::kBN, kLd = Cfg::kLd;
   extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -373,9 +375,9 @@ __global__ void __launch_bounds__(128) attn_bwd_q_kernel(const AttnParams p) {
 #pragma unroll
     for (int n = 0; n < BN / 8; ++n) {
       uint4 b0 = make_uint4(0, 0, 0, 0), b1 = make_uint4(0, 0, 0, 0);
-      if (p.drop.thr != 0) {
-        b0 = dropout_bits8(p.drop, p.drop_stream, (ridx0 + j0 + n * 8) >> 3);
-        b1 = dropout_bits8(p.drop, p.drop_stream, (ridx1 + j0 + n * 8) >> 3);
+      if (drop.thr != 0) {
+        b0 = dropout_bits8(drop, p.drop_stream, (ridx0 + j0 + n * 8) >> 3);
+        b1 = dropout_bits8(drop, p.drop_stream, (ridx1 + j0 + n * 8) >> 3);
       }
       float pd[4];
 #pragma unroll
@@ -385,10 +387,10 @@ __global__ void __launch_bounds__(128) attn_bwd_q_kernel(const AttnParams p) {
         float pr = (col < p.Lk) ? exp2f(s[n][e] * p.scale_log2 - lse) : 0.f;
         float dpr = dp[n][e];
         float prd = pr;
-        if (p.drop.thr != 0) {
-          const bool keep = dropout_keep((e < 2) ? b0 : b1, 2 * t4 + (e & 1), p.drop.thr);
-          prd = keep ? pr * p.drop.scale : 0.f;
-          dpr = keep ? dpr * p.drop.scale : 0.f;
+        if (drop.thr != 0) {
+          const bool keep = dropout_keep((e < 2) ? b0 : b1, 2 * t4 + (e & 1), drop.thr);
+          prd = keep ? pr * drop.scale : 0.f;
+          dpr = keep ? dpr * drop.scale : 0.f;
         }
         pd[e] = prd;
         s[n][e] = pr * (dpr - del);  // dS (without the softmax scale)
@@ -602,8 +604,8 @@ static AttnParams make_params(const b200b_attn_args* a) {
   p.Lkp = (a->len_k + 7) & ~7;
   p.scale = 1.0f / sqrtf((float)a->head_dim);
   p.scale_log2 = p.scale * 1.4426950408889634f;
-  p.drop = make_dropout_cfg(a->dropout_p, a->seed);
   p.drop_stream = a->dropout_stream;
+  p.drop = make_dropout_cfg(a->dropout_p, a->seed, &p.drop_stream);
   return p;
 }
 

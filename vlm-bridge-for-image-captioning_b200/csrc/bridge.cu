@@ -24,7 +24,7 @@ struct Carver {
 };
 
 struct Dims {
-  int B, L, Nv, D, Dv, F, Hc, Hs, nb;
+  int B, L, Nv, D, Dv, F, Hc, Hs, nb, flags;
   size_t T, Tv;
   int dc, ds;  // head dims
 };
@@ -36,7 +36,7 @@ static int read_dims(const b200b_bridge_dims* d, Dims* o, const char* what) {
   }
   o->B = d->batch; o->L = d->len_text; o->Nv = d->len_vision;
   o->D = d->dim; o->Dv = d->dim_vision; o->F = d->dim_ffn;
-  o->Hc = d->heads_cross; o->Hs = d->heads_self; o->nb = d->num_blocks;
+  o->Hc = d->heads_cross; o->Hs = d->heads_self; o->nb = d->num_blocks; o->flags = d->flags;
   if (o->B <= 0 || o->L <= 0 || o->Nv <= 0 || o->D <= 0 || o->Dv <= 0 || o->F <= 0 || o->Hc <= 0 || o->Hs <= 0 ||
       o->nb <= 0) {
     set_last_error("%s: all dims must be positive", what);
@@ -226,6 +226,8 @@ extern "C" int b200b_bridge_block_forward(const b200b_bridge_dims* dims, int i, 
     return B200B_ERR_WORKSPACE;
   }
   const int T = (int)d.T, D = d.D, F = d.F;
+  // B200B_BRIDGE_SEED_INDIRECT: `seed` holds a device pointer; every kernel reads the seed itself
+  const uint32_t ind = (d.flags & B200B_BRIDGE_SEED_INDIRECT) ? B200B_SEED_INDIRECT : 0u;
   const long long ldkv = 2LL * D * d.nb;
   const __nv_bfloat16* kblk = reinterpret_cast<const __nv_bfloat16*>(kv) + (size_t)2 * D * i;
   const float eps = 1e-5f;
@@ -235,7 +237,7 @@ extern "C" int b200b_bridge_block_forward(const b200b_bridge_dims* dims, int i, 
   B200B_TRY(gemm(s.xn1, 0, D, w->wq_c, 0, D, T, D, D, B200B_EPI_BF16_BIAS, s.q, D, w->bq_c, nullptr, nullptr, 0, 0.f, 0,
                  0, st));
   B200B_TRY(attn(false, s.q, D, kblk, ldkv, kblk + D, ldkv, s.o1, D, s.lse1, nullptr, nullptr, 0, nullptr, 0, nullptr, 0,
-                 nullptr, 0, d.B, d.Hc, d.L, d.Nv, d.dc, p, seed, ds_cross(i), st));
+                 nullptr, 0, d.B, d.Hc, d.L, d.Nv, d.dc, p, seed, (ds_cross(i) | ind), st));
   B200B_TRY(gemm(s.o1, 0, D, w->wo_c, 0, D, T, D, D, B200B_EPI_F32_BIAS_RESID, s.x1, D, w->bo_c, x_in, nullptr, 0, 0.f,
                  0, 0, st));
   // 2. self-attention (non-causal, unmasked)                                 (:326-328)
@@ -243,22 +245,23 @@ extern "C" int b200b_bridge_block_forward(const b200b_bridge_dims* dims, int i, 
   B200B_TRY(gemm(s.xn2, 0, D, w->wqkv_s, 0, D, T, 3 * D, D, B200B_EPI_BF16_BIAS, s.qkv, 3 * D, w->bqkv_s, nullptr,
                  nullptr, 0, 0.f, 0, 0, st));
   B200B_TRY(attn(false, s.qkv, 3 * D, s.qkv + D, 3 * D, s.qkv + 2 * D, 3 * D, s.o2, D, s.lse2, nullptr, nullptr, 0,
-                 nullptr, 0, nullptr, 0, nullptr, 0, d.B, d.Hs, d.L, d.L, d.ds, p, seed, ds_self(i), st));
+                 nullptr, 0, nullptr, 0, nullptr, 0, d.B, d.Hs, d.L, d.L, d.ds, p, seed, (ds_self(i) | ind), st));
   B200B_TRY(gemm(s.o2, 0, D, w->wo_s, 0, D, T, D, D, B200B_EPI_F32_BIAS_RESID, s.x2, D, w->bo_s, s.x1, nullptr, 0, 0.f,
                  0, 0, st));
   // 3. FFN: x3 = x2 + drop(W_2 * drop(gelu(W_1 * LN(x2))))                    (:331-333)
   B200B_TRY(b200b_layernorm_fwd_rows(s.x2, w->ln_f_g, w->ln_f_b, s.xn3, s.mean3, s.rstd3, T, D, eps, st));
   B200B_TRY(gemm(s.xn3, 0, D, w->w1, 0, D, T, F, D, B200B_EPI_BF16_BIAS_GELU, s.h, F, w->b1, nullptr, s.u, F, p, seed,
-                 ds_ffn_h(i), st));
+                 (ds_ffn_h(i) | ind), st));
   B200B_TRY(gemm(s.h, 0, F, w->w2, 0, F, T, D, F, B200B_EPI_F32_BIAS_RESID, x_out, D, w->b2, s.x2, nullptr, 0, p, seed,
-                 ds_ffn_o(i), st));
+                 (ds_ffn_o(i) | ind), st));
   return B200B_OK;
 }
 
 extern "C" int b200b_bridge_block_backward(const b200b_bridge_dims* dims, int i, const b200b_block_weights* w,
                                            const float* x_in, const void* kv, const void* saved, const float* d_out,
                                            float* d_in, void* dkv, const b200b_block_grads* g, void* workspace,
-                                           size_t workspace_bytes, float p, uint64_t seed, void* stream_) {
+                                           size_t workspace_bytes, float p, uint64_t seed,
+                                           const b200b_grad_notify* notify, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   Dims d;
   B200B_TRY(read_dims(dims, &d, "block_backward"));
@@ -273,10 +276,17 @@ extern "C" int b200b_bridge_block_backward(const b200b_bridge_dims* dims, int i,
     return B200B_ERR_WORKSPACE;
   }
   const int T = (int)d.T, D = d.D, F = d.F;
+  // B200B_BRIDGE_SEED_INDIRECT: `seed` holds a device pointer; every kernel reads the seed itself
+  const uint32_t ind = (d.flags & B200B_BRIDGE_SEED_INDIRECT) ? B200B_SEED_INDIRECT : 0u;
   const long long ldkv = 2LL * D * d.nb;
   const __nv_bfloat16* kblk = reinterpret_cast<const __nv_bfloat16*>(kv) + (size_t)2 * D * i;
   __nv_bfloat16* dkblk = reinterpret_cast<__nv_bfloat16*>(dkv) + (size_t)2 * D * i;
-  const int EB = B200B_EPI_BF16_BIAS, EF = B200B_EPI_F32;
+  const int EB = B200B_EPI_BF16_BIAS;
+  // weight gradients: fp32, or bf16 (no bias operand) when the caller exchanges them in bf16
+  const int EW = (d.flags & B200B_BRIDGE_WGRAD_BF16) ? B200B_EPI_BF16_BIAS : B200B_EPI_F32;
+  auto ready = [&](const void* grad, long long elems) {
+    if (notify != nullptr && notify->fn != nullptr) notify->fn(notify->user, grad, elems);
+  };
 
   const int rchunks = b200b_row_chunks(T);
   if (rchunks <= 0 || rchunks > kMaxRowChunks) {
@@ -288,14 +298,16 @@ extern "C" int b200b_bridge_block_backward(const b200b_bridge_dims* dims, int i,
 
   // ---- FFN ----
   // d(ffn.3 out) = dropout-bwd(bf16(d_out)); its column sums are the ffn.3 bias gradient
-  B200B_TRY(b200b_cast_bf16_colsum(d_out, ws.dy, ws.p_cast, T, D, p, seed, ds_ffn_o(i), st));
+  B200B_TRY(b200b_cast_bf16_colsum(d_out, ws.dy, ws.p_cast, T, D, p, seed, (ds_ffn_o(i) | ind), st));
   fin.add(ws.p_cast, g->b2, D, rchunks, D);
-  B200B_TRY(gemm(ws.dy, 1, D, s.h, 1, F, D, F, T, EF, g->w2, F, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  B200B_TRY(gemm(ws.dy, 1, D, s.h, 1, F, D, F, T, EW, g->w2, F, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  ready(g->w2, (long long)D * F);
   B200B_TRY(gemm(ws.dy, 0, D, w->w2, 1, F, T, F, D, B200B_EPI_BF16_DGELU, ws.du, F, nullptr, nullptr, s.u, F, p, seed,
-                 ds_ffn_h(i), st));
+                 (ds_ffn_h(i) | ind), st));
   B200B_TRY(b200b_colsum_partials(ws.du, F, T, F, ws.p_du, &ch, st));
   fin.add(ws.p_du, g->b1, F, ch, F);
-  B200B_TRY(gemm(ws.du, 1, F, s.xn3, 1, D, F, D, T, EF, g->w1, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  B200B_TRY(gemm(ws.du, 1, F, s.xn3, 1, D, F, D, T, EW, g->w1, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  ready(g->w1, (long long)F * D);
   B200B_TRY(gemm(ws.du, 0, F, w->w1, 1, D, T, D, F, EB, ws.dxn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
   // ln_ffn backward (+ residual gradient d_out) -> dx; bf16(dx) = gradient of the self-attention W_o output
   B200B_TRY(b200b_layernorm_bwd_fused(ws.dxn, s.x2, s.mean3, s.rstd3, w->ln_f_g, d_out, ws.dx, ws.dy, ws.p_lnf, T, D, st));
@@ -303,15 +315,17 @@ extern "C" int b200b_bridge_block_backward(const b200b_bridge_dims* dims, int i,
   fin.add(ws.p_lnf + D, g->ln_f_g, D, rchunks, 3LL * D);
   fin.add(ws.p_lnf + 2 * D, g->bo_s, D, rchunks, 3LL * D);
   // ---- self-attention ----
-  B200B_TRY(gemm(ws.dy, 1, D, s.o2, 1, D, D, D, T, EF, g->wo_s, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  B200B_TRY(gemm(ws.dy, 1, D, s.o2, 1, D, D, D, T, EW, g->wo_s, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  ready(g->wo_s, (long long)D * D);
   B200B_TRY(gemm(ws.dy, 0, D, w->wo_s, 1, D, T, D, D, EB, ws.dattn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
   B200B_TRY(attn(true, s.qkv, 3 * D, s.qkv + D, 3 * D, s.qkv + 2 * D, 3 * D, s.o2, D, s.lse2, ws.dattn, ws.dqkv, 3 * D,
                  ws.dqkv + D, 3 * D, ws.dqkv + 2 * D, 3 * D, ws.attn_ws, ws.attn_ws_bytes, d.B, d.Hs, d.L, d.L, d.ds, p,
-                 seed, ds_self(i), st));
+                 seed, (ds_self(i) | ind), st));
   B200B_TRY(b200b_colsum_partials(ws.dqkv, 3 * D, T, 3 * D, ws.p_dqkv, &ch, st));
   fin.add(ws.p_dqkv, g->bqkv_s, 3 * D, ch, 3LL * D);
-  B200B_TRY(gemm(ws.dqkv, 1, 3 * D, s.xn2, 1, D, 3 * D, D, T, EF, g->wqkv_s, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0,
+  B200B_TRY(gemm(ws.dqkv, 1, 3 * D, s.xn2, 1, D, 3 * D, D, T, EW, g->wqkv_s, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0,
                  st));
+  ready(g->wqkv_s, 3LL * D * D);
   B200B_TRY(gemm(ws.dqkv, 0, 3 * D, w->wqkv_s, 1, D, T, D, 3 * D, EB, ws.dxn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0,
                  st));
   B200B_TRY(b200b_layernorm_bwd_fused(ws.dxn, s.x1, s.mean2, s.rstd2, w->ln_s_g, ws.dx, ws.dx, ws.dy, ws.p_lns, T, D, st));
@@ -319,14 +333,16 @@ extern "C" int b200b_bridge_block_backward(const b200b_bridge_dims* dims, int i,
   fin.add(ws.p_lns + D, g->ln_s_g, D, rchunks, 3LL * D);
   fin.add(ws.p_lns + 2 * D, g->bo_c, D, rchunks, 3LL * D);
   // ---- cross-attention ----
-  B200B_TRY(gemm(ws.dy, 1, D, s.o1, 1, D, D, D, T, EF, g->wo_c, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  B200B_TRY(gemm(ws.dy, 1, D, s.o1, 1, D, D, D, T, EW, g->wo_c, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  ready(g->wo_c, (long long)D * D);
   B200B_TRY(gemm(ws.dy, 0, D, w->wo_c, 1, D, T, D, D, EB, ws.dattn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
   __nv_bfloat16* dq = ws.dqkv;  // [T, D]
   B200B_TRY(attn(true, s.q, D, kblk, ldkv, kblk + D, ldkv, s.o1, D, s.lse1, ws.dattn, dq, D, dkblk, ldkv, dkblk + D, ldkv,
-                 ws.attn_ws, ws.attn_ws_bytes, d.B, d.Hc, d.L, d.Nv, d.dc, p, seed, ds_cross(i), st));
+                 ws.attn_ws, ws.attn_ws_bytes, d.B, d.Hc, d.L, d.Nv, d.dc, p, seed, (ds_cross(i) | ind), st));
   B200B_TRY(b200b_colsum_partials(dq, D, T, D, ws.p_dq, &ch, st));
   fin.add(ws.p_dq, g->bq_c, D, ch, D);
-  B200B_TRY(gemm(dq, 1, D, s.xn1, 1, D, D, D, T, EF, g->wq_c, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  B200B_TRY(gemm(dq, 1, D, s.xn1, 1, D, D, D, T, EW, g->wq_c, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  ready(g->wq_c, (long long)D * D);
   B200B_TRY(gemm(dq, 0, D, w->wq_c, 1, D, T, D, D, EB, ws.dxn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
   // ln_cross backward: d_in (if wanted) = dx + LN input gradient; dgamma / dbeta always
   B200B_TRY(b200b_layernorm_bwd_fused(ws.dxn, x_in, s.mean1, s.rstd1, w->ln_c_g, ws.dx, d_in, nullptr, ws.p_lnc, T, D, st));
@@ -336,7 +352,7 @@ extern "C" int b200b_bridge_block_backward(const b200b_bridge_dims* dims, int i,
 }
 
 extern "C" int b200b_bridge_kv_backward(const b200b_bridge_dims* dims, const void* vision_bf16, const void* dkv,
-                                        float* dwkv_all, float* dbkv_all, void* workspace, size_t workspace_bytes,
+                                        void* dwkv_all, float* dbkv_all, void* workspace, size_t workspace_bytes,
                                         void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   Dims d;
@@ -356,6 +372,7 @@ extern "C" int b200b_bridge_kv_backward(const b200b_bridge_dims* dims, const voi
   b200b_colsum_task t;
   t.partials = ws.p_dkv; t.out = dbkv_all; t.cols = n; t.chunks = ch; t.chunk_stride = n;
   B200B_TRY(b200b_colsum_finalize(&t, 1, st));
-  return gemm(dkv, 1, n, vision_bf16, 1, d.Dv, n, d.Dv, (int)d.Tv, B200B_EPI_F32, dwkv_all, d.Dv, nullptr, nullptr,
+  const int EW = (d.flags & B200B_BRIDGE_WGRAD_BF16) ? B200B_EPI_BF16_BIAS : B200B_EPI_F32;
+  return gemm(dkv, 1, n, vision_bf16, 1, d.Dv, n, d.Dv, (int)d.Tv, EW, dwkv_all, d.Dv, nullptr, nullptr,
               nullptr, 0, 0.f, 0, 0, st);
 }

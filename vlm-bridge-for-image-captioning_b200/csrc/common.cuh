@@ -93,7 +93,18 @@ struct DropoutCfg {
   uint32_t thr;        // 0 = dropout disabled
   float scale;         // 1 / (1 - p)
   uint32_t seed_lo, seed_hi;
-};
+  const unsigned long long* seed_ptr;  // non-null: the seed is read from device memory at kernel start
+};                                     // (B200B_SEED_INDIRECT: lets a captured CUDA graph draw new masks per replay)
+
+// the configuration with its seed resolved; call once per thread at kernel start
+__device__ __forceinline__ DropoutCfg dropout_resolve(DropoutCfg d) {
+  if (d.seed_ptr != nullptr && d.thr != 0) {
+    const unsigned long long s = __ldg(d.seed_ptr);
+    d.seed_lo = (uint32_t)s;
+    d.seed_hi = (uint32_t)(s >> 32);
+  }
+  return d;
+}
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;

@@ -196,7 +196,8 @@ static int colsum_chunks(int rows, int cols, int num_sms) {
 // bf16 rounding, as autograd does on the bf16 gradient).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
-                                                        long long n8, DropoutCfg drop, uint32_t stream) {
+                                                        long long n8, DropoutCfg drop_in, uint32_t stream) {
+  const DropoutCfg drop = dropout_resolve(drop_in);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n8; g += stride) {
     const float4 a = __ldcs(reinterpret_cast<const float4*>(in) + 2 * g);
@@ -415,7 +416,8 @@ template <int GPT>
 __global__ void __launch_bounds__(288) cast_colsum_row_kernel(const float* __restrict__ in,
                                                               __nv_bfloat16* __restrict__ out,
                                                               float* __restrict__ partials, int rows, int dim,
-                                                              DropoutCfg drop, uint32_t stream) {
+                                                              DropoutCfg drop_in, uint32_t stream) {
+  const DropoutCfg drop = dropout_resolve(drop_in);
   float ps[GPT][8];
 #pragma unroll
   for (int i = 0; i < GPT; ++i)
@@ -463,32 +465,49 @@ struct FinalizeTasks {
   b200b_colsum_task t[B200B_MAX_COLSUM_TASKS];
   int n;
 };
-// Block = 32 columns x 16 chunk-lanes: lane ty sums chunks ty, ty+16, ... (4 loads in flight), then
-// the 16 lanes are combined through shared memory in a fixed order.
-__global__ void __launch_bounds__(512) colsum_finalize_multi_kernel(const FinalizeTasks tasks) {
+// Block = 128 columns (32 lanes x float4) x 8 chunk-lanes: lane ty sums chunks ty, ty+8, ... with 8
+// independent 16-byte loads in flight, then the 8 lanes are combined through shared memory in a
+// fixed order (deterministic).
+__global__ void __launch_bounds__(256) colsum_finalize_multi_kernel(const FinalizeTasks tasks) {
   const b200b_colsum_task& t = tasks.t[blockIdx.y];
+  if (blockIdx.x * 128 >= t.cols) return;  // whole block out of range for this (shorter) task
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
-  if (blockIdx.x * 32 >= t.cols) return;  // whole block out of range for this (shorter) task
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  const int c = blockIdx.x * 128 + 4 * tx;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c < t.cols) {
+    const float* base = t.partials + c;
     int j = ty;
-    for (; j + 48 < t.chunks; j += 64) {
-      s0 += t.partials[(size_t)j * t.chunk_stride + c];
-      s1 += t.partials[(size_t)(j + 16) * t.chunk_stride + c];
-      s2 += t.partials[(size_t)(j + 32) * t.chunk_stride + c];
-      s3 += t.partials[(size_t)(j + 48) * t.chunk_stride + c];
+    for (; j + 56 < t.chunks; j += 64) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(base + (size_t)(j + 8 * u) * t.chunk_stride));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
     }
-    for (; j < t.chunks; j += 16) s0 += t.partials[(size_t)j * t.chunk_stride + c];
+    for (; j < t.chunks; j += 8) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(base + (size_t)j * t.chunk_stride));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
   }
-  __shared__ float sh[16][33];
-  sh[ty][tx] = (s0 + s1) + (s2 + s3);
+  __shared__ float4 sh[8][32];
+  sh[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && c < t.cols) {
-    float s = 0.f;
+    float4 r = sh[0][tx];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) s += sh[k][tx];
-    t.out[c] = s;
+    for (int k = 1; k < 8; ++k) { const float4 v = sh[k][tx]; r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w; }
+    *reinterpret_cast<float4*>(t.out + c) = r;
+  }
+}
+
+// out f32 = scale * in bf16 (exchanged gradient bucket -> .grad)
+__global__ void __launch_bounds__(256) bf16_to_f32_kernel(const uint4* __restrict__ in, float4* __restrict__ out,
+                                                          long long n8, float scale) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n8; g += stride) {
+    const uint4 v = __ldcs(in + g);
+    __stcs(out + 2 * g, make_float4(bf16_lo(v.x) * scale, bf16_hi(v.x) * scale, bf16_lo(v.y) * scale, bf16_hi(v.y) * scale));
+    __stcs(out + 2 * g + 1, make_float4(bf16_lo(v.z) * scale, bf16_hi(v.z) * scale, bf16_lo(v.w) * scale, bf16_hi(v.w) * scale));
   }
 }
 
@@ -642,8 +661,9 @@ extern "C" int b200b_cast_bf16(const float* in, void* out_bf16, int64_t n, float
   long long blocks = (n8 + 255) / 256;
   const long long cap = (long long)num_sms * 8;  // 8 resident CTAs of 256 threads per SM, grid-stride beyond
   if (blocks > cap) blocks = cap;
-  cast_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out_bf16), n8,
-                                                    make_dropout_cfg(dropout_p, seed), dropout_stream);
+  const DropoutCfg dc = make_dropout_cfg(dropout_p, seed, &dropout_stream);
+  cast_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out_bf16), n8, dc,
+                                                    dropout_stream);
   return check_launch("cast_bf16", stream);
 }
 
@@ -750,7 +770,7 @@ extern "C" int b200b_cast_bf16_colsum(const float* in, void* out_bf16, float* pa
   }
   const int grid = b200b_row_chunks(rows);
   if (grid <= 0) return B200B_ERR_DEVICE;
-  const DropoutCfg dc = make_dropout_cfg(dropout_p, seed);
+  const DropoutCfg dc = make_dropout_cfg(dropout_p, seed, &dropout_stream);
   const int gpt = (dim / 8 + 287) / 288;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   if (gpt <= 1) cast_colsum_row_kernel<1><<<grid, 288, 0, stream>>>(in, o, partials, rows, dim, dc, dropout_stream);
@@ -796,14 +816,41 @@ extern "C" int b200b_colsum_finalize(const b200b_colsum_task* tasks, int ntasks,
   ft.n = ntasks;
   int max_cols = 0;
   for (int i = 0; i < ntasks; ++i) {
-    if (!tasks[i].partials || !tasks[i].out || tasks[i].cols <= 0 || tasks[i].chunks <= 0) {
+    if (!tasks[i].partials || !tasks[i].out || tasks[i].cols <= 0 || tasks[i].chunks <= 0 || (tasks[i].cols % 4) ||
+        (tasks[i].chunk_stride % 4) || !al16(tasks[i].partials) || !al16(tasks[i].out)) {
       set_last_error("colsum_finalize: bad task %d", i);
       return B200B_ERR_ARG;
     }
     ft.t[i] = tasks[i];
     if (tasks[i].cols > max_cols) max_cols = tasks[i].cols;
   }
-  dim3 grid((max_cols + 31) / 32, ntasks);
-  colsum_finalize_multi_kernel<<<grid, 512, 0, stream>>>(ft);
+  dim3 grid((max_cols + 127) / 128, ntasks);
+  colsum_finalize_multi_kernel<<<grid, 256, 0, stream>>>(ft);
   return check_launch("colsum_final", stream);
+}
+
+extern "C" int b200b_bf16_to_f32(const void* in_bf16, float* out, int64_t n, float scale, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!in_bf16 || !out) {
+    set_last_error("bf16_to_f32: null argument");
+    return B200B_ERR_ARG;
+  }
+  if (n <= 0 || (n % 8) != 0) {
+    set_last_error("bf16_to_f32: n must be a positive multiple of 8 (n=%lld)", (long long)n);
+    return B200B_ERR_SHAPE;
+  }
+  if (!al16(in_bf16) || !al16(out)) {
+    set_last_error("bf16_to_f32: misaligned pointer");
+    return B200B_ERR_ALIGN;
+  }
+  int num_sms = 0;
+  int rc = device_sm_count(&num_sms);
+  if (rc != B200B_OK) return rc;
+  const long long n8 = n / 8;
+  long long blocks = (n8 + 255) / 256;
+  const long long cap = (long long)num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  bf16_to_f32_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(in_bf16),
+                                                      reinterpret_cast<float4*>(out), n8, scale);
+  return check_launch("bf16_to_f32", stream);
 }

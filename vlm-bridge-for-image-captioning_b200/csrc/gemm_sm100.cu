@@ -125,8 +125,8 @@ static __device__ __noinline__ uint4 dropout_bits8_call(uint32_t seed_lo, uint32
 // Dropout decisions of one group: the two lanes that share an 8-element dropout group (lane ^ 1)
 // each run Philox for one of two consecutive passes and swap the halves they do not need.
 // Executed by all 32 lanes (shuffles); dropout disabled -> thr == 0 keeps everything.
-__device__ __forceinline__ void epi_dropout_bits(const GemmKernelParams& p, int row0, int col, int r_sub, int cg,
-                                                 uint2 (&w)[kGroupPasses]) {
+__device__ __forceinline__ void epi_dropout_bits(const GemmKernelParams& p, uint2 seed, int row0, int col, int r_sub,
+                                                 int cg, uint2 (&w)[kGroupPasses]) {
 #pragma unroll
   for (int i = 0; i < kGroupPasses; ++i) w[i] = make_uint2(0u, 0u);
   if (p.drop.thr == 0) return;  // warp-uniform
@@ -135,7 +135,7 @@ __device__ __forceinline__ void epi_dropout_bits(const GemmKernelParams& p, int 
   for (int pp = 0; pp < kGroupPasses; pp += 2) {
     const int row = row0 + 4 * (pp + (odd ? 1 : 0)) + r_sub;
     const uint64_t group = ((uint64_t)row * (uint64_t)p.n + (uint64_t)col) >> 3;
-    const uint4 b = dropout_bits8_call(p.drop.seed_lo, p.drop.seed_hi, p.drop_stream, (uint32_t)group,
+    const uint4 b = dropout_bits8_call(seed.x, seed.y, p.drop_stream, (uint32_t)group,
                                        (uint32_t)(group >> 32));
     const uint32_t r0 = __shfl_xor_sync(0xffffffffu, odd ? b.x : b.z, 1);
     const uint32_t r1 = __shfl_xor_sync(0xffffffffu, odd ? b.y : b.w, 1);
@@ -240,7 +240,8 @@ __device__ __forceinline__ void drain_prefetch(const GemmKernelParams& p, int ro
 template <int BLOCK_N, int EPI>
 __device__ __forceinline__ void drain_accumulator(const GemmKernelParams& p, uint32_t t_row, int row0 /*of this warp*/,
                                                   int n_idx, float* stage /*this warp's tile*/, int lane, int half,
-                                                  EpiOperands<EPI>& ops /*prefetched for the first group*/) {
+                                                  EpiOperands<EPI>& ops /*prefetched for the first group*/,
+                                                  uint2 seed /*resolved dropout seed*/) {
   const int r_sub = lane >> 3, cg = lane & 7;
   constexpr int kChunks = BLOCK_N / 64;  // chunks per warp
 #pragma unroll 1
@@ -268,7 +269,7 @@ __device__ __forceinline__ void drain_accumulator(const GemmKernelParams& p, uin
         if (!(last_grp && i + 1 == kChunks)) epi_fetch<EPI>(p, nrow0, ncol, r_sub, nxt);
       }
       uint2 w[kGroupPasses];
-      if constexpr (kEpiHasDropout<EPI>) epi_dropout_bits(p, grow0, col, r_sub, cg, w);
+      if constexpr (kEpiHasDropout<EPI>) epi_dropout_bits(p, seed, grow0, col, r_sub, cg, w);
 #pragma unroll
       for (int pass = 0; pass < kGroupPasses; ++pass) {
         const int r = 4 * (kGroupPasses * grp + pass) + r_sub;
@@ -420,6 +421,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const int half = warp >> 2;
     float* epi_stage =
         reinterpret_cast<float*>(smem_gen + (size_t)kStages * Cfg::kStageBytes) + warp * 32 * kEpiLd;
+    const DropoutCfg drop = dropout_resolve(p.drop);
+    const uint2 seed = make_uint2(drop.seed_lo, drop.seed_hi);
     int iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
       const int acc = iter & 1;
@@ -431,7 +434,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       mbar_wait_a(tfull0 + 8u * acc, acc_phase);
       tc_fence_after();
       drain_accumulator<BLOCK_N, EPI>(p, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N),
-                                      m_idx + quad * 32, n_idx, epi_stage, lane, half, ops);
+                                      m_idx + quad * 32, n_idx, epi_stage, lane, half, ops, seed);
       tc_fence_before();
       mbar_arrive_a(tempty0 + 8u * acc);
     }
@@ -456,7 +459,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 // ================================================================================================
 template <int BLOCK_N>
 struct GemmPairCfg {
-  static constexpr int kStages = (BLOCK_N == 256) ? 6 : 8;
+  static constexpr int kStages = (BLOCK_N == 256) ? 5 : 7;  // leaves ~25 KB of the SM for a co-resident exchange CTA
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;          // this CTA's 128 rows
   static constexpr uint32_t kBBytes = (BLOCK_N / 2) * kBlockK * 2;    // this CTA's half of B
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
@@ -588,6 +591,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     const int half = warp >> 2;
     float* epi_stage =
         reinterpret_cast<float*>(smem_gen + (size_t)kStages * Cfg::kStageBytes) + warp * 32 * kEpiLd;
+    const DropoutCfg drop = dropout_resolve(p.drop);
+    const uint2 seed = make_uint2(drop.seed_lo, drop.seed_hi);
     int iter = 0;
     for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++iter) {
       const int acc = iter & 1;
@@ -599,7 +604,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       mbar_wait_a(tfull0 + 8u * acc, acc_phase);
       tc_fence_after();
       drain_accumulator<BLOCK_N, EPI>(p, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N),
-                                      m_idx + quad * 32, n_idx, epi_stage, lane, half, ops);
+                                      m_idx + quad * 32, n_idx, epi_stage, lane, half, ops, seed);
       tc_fence_before();
       mbar_arrive_cluster_a(tempty0_even + 8u * acc);  // the even CTA's MMA thread owns the accumulator handshake
     }
@@ -836,8 +841,8 @@ extern "C" int b200b_gemm(const b200b_gemm_args* a, void* stream_) {
   p.bias = a->bias;
   p.resid = a->resid; p.ldr = a->ldr;
   p.beta = a->beta;
-  p.drop = make_dropout_cfg(a->dropout_p, a->seed);
   p.drop_stream = a->dropout_stream;
+  p.drop = make_dropout_cfg(a->dropout_p, a->seed, &p.drop_stream);
   static const int debug_mode = [] { const char* e = getenv("B200B_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug_mode = debug_mode;
 

@@ -16,8 +16,16 @@ int check_launch(const char* what, cudaStream_t stream);
 // SM count of the current device (cached per device); fails on non-sm_100 devices
 int device_sm_count(int* out);
 
-inline DropoutCfg make_dropout_cfg(float p, uint64_t seed) {
+// `stream` is the caller's dropout stream id: its B200B_SEED_INDIRECT bit says that `seed` is a device
+// pointer to the 64-bit seed; the bit is cleared from `stream` here.
+inline DropoutCfg make_dropout_cfg(float p, uint64_t seed, uint32_t* stream) {
   DropoutCfg d;
+  d.seed_ptr = nullptr;
+  if (stream != nullptr && (*stream & 0x80000000u)) {
+    *stream &= 0x7fffffffu;
+    d.seed_ptr = reinterpret_cast<const unsigned long long*>(static_cast<uintptr_t>(seed));
+    seed = 0;
+  }
   if (p > 0.0f) {
     uint32_t thr = (uint32_t)(p * 65536.0f + 0.5f);
     if (thr < 1) thr = 1;
