@@ -198,6 +198,21 @@ int b200b_attention_fwd(const b200b_attn_args* args, void* stream);
 size_t b200b_attention_bwd_workspace_bytes(int batch, int heads, int len_q, int len_k);
 int b200b_attention_bwd(const b200b_attn_args* args, void* stream);
 
+/* Decode path over a per-image cached vision K/V (the reference re-projects
+ * the unchanged image inside every step of full_model.py:241-261). b200b_kv_cache_pack turns the
+ * projection output kv bf16 [batch*len_k, num_blocks*2*heads*head_dim] (block i: K columns, then V
+ * columns) into the decode layout [batch][num_blocks][heads][2][len_k][head_dim+8]: per (image,
+ * block, head) the K rows then the V rows, padded to the shared-memory row pitch of the decode
+ * kernel, so a 16-key tile is one contiguous TMA bulk copy. b200b_attention_decode_packed is
+ * b200b_attention_fwd for 1 <= len_q <= 64 query rows per image against block `block_index` of
+ * that cache (no dropout; lse may be NULL). */
+size_t b200b_kv_cache_packed_bytes(int batch, int len_k, int heads, int head_dim, int num_blocks);
+int b200b_kv_cache_pack(const void* kv, int64_t ldkv, void* packed, int batch, int len_k, int heads,
+                        int head_dim, int num_blocks, void* stream);
+int b200b_attention_decode_packed(const void* q, int64_t ldq, const void* kv_packed, int block_index,
+                                  int num_blocks, void* o, int64_t ldo, float* lse, int batch, int heads,
+                                  int len_q, int len_k, int head_dim, void* stream);
+
 /* ------------------------------------------------------------------------------------------- *
  * Whole-block entry points: one call enqueues every kernel of a BridgeBlock forward or backward
  * (reference: BridgeBlock.forward, bridge_module.py:300-335, and the autograd graph it builds).
@@ -224,6 +239,9 @@ typedef struct b200b_bridge_dims {
  * that every dropout kernel reads when it runs, so that a captured CUDA graph draws fresh masks on
  * every replay (the caller advances the value between replays, e.g. with a captured add kernel). */
 #define B200B_BRIDGE_SEED_INDIRECT 2
+/* flags (block_forward only): `kv` is the packed decode cache written by b200b_kv_cache_pack, not the
+ * row-major projection output. Needs dropout_p == 0 and len_text <= 64. */
+#define B200B_BRIDGE_KV_PACKED 4
 /* The same for the individual operators: OR this bit into `dropout_stream` and pass the device
  * pointer (cast to uint64_t) as `seed`. */
 #define B200B_SEED_INDIRECT 0x80000000u

@@ -21,6 +21,14 @@ CASES = [
     ("attn", 8, 8, 128, 257, 288, 0.0),    # C2 cross
     ("attn", 8, 18, 128, 128, 128, 0.0),   # C2 self
     ("attn", 1, 8, 5, 257, 288, 0.0),      # decode-like short prefix
+    ("attn", 32, 8, 1, 257, 288, 0.0),     # C4 decode steps (K/V-streaming kernel): 1, 2, 3, 4 query row groups
+    ("attn", 32, 8, 17, 257, 288, 0.0),
+    ("attn", 4, 8, 33, 257, 288, 0.0),
+    ("attn", 4, 8, 48, 257, 288, 0.0),
+    ("attn", 32, 8, 64, 257, 288, 0.0),
+    ("attn", 2, 8, 20, 5, 288, 0.0),       # one key tile: the second key split sees no key
+    ("attn", 2, 18, 3, 3, 128, 0.0),       # self-attention of a 3-token prefix
+    ("attn", 2, 8, 64, 1370, 288, 0.0),    # long K/V: many ring wrap-arounds
     ("attn", 2, 8, 128, 1370, 288, 0.0),   # C5 vision length
     ("attn", 2, 8, 64, 257, 288, 0.1),     # dropout
     ("attn", 2, 18, 64, 64, 128, 0.1),

@@ -134,6 +134,13 @@ def _declare(lib) -> None:
     lib.b200b_colsum_finalize.argtypes = [C.POINTER(ColsumTask), C.c_int, C.c_void_p]
     lib.b200b_attention_fwd.restype = C.c_int
     lib.b200b_attention_fwd.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
+    lib.b200b_kv_cache_packed_bytes.restype = C.c_size_t
+    lib.b200b_kv_cache_packed_bytes.argtypes = [C.c_int] * 5
+    lib.b200b_kv_cache_pack.restype = C.c_int
+    lib.b200b_kv_cache_pack.argtypes = [C.c_void_p, C.c_int64, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
+    lib.b200b_attention_decode_packed.restype = C.c_int
+    lib.b200b_attention_decode_packed.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                                  C.c_int64, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
     lib.b200b_attention_bwd_workspace_bytes.restype = C.c_size_t
     lib.b200b_attention_bwd_workspace_bytes.argtypes = [C.c_int] * 4
     lib.b200b_attention_bwd.restype = C.c_int

@@ -17,6 +17,7 @@
 // P from the saved log-sum-exp, forms dS, accumulates dQ and spills P(dropped) and dS as bf16 to a
 // scratch [B,H,Lq,Lkp]; and a key-major pass dV = P^T dO, dK = dS^T Q that reads that scratch.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -38,6 +39,7 @@ struct AttnParams {
   __nv_bfloat16* p_scr;                    // [B,H,Lq,Lkp] dropped probabilities
   __nv_bfloat16* ds_scr;                   // [B,H,Lq,Lkp] dS (unscaled)
   int B, H, Lq, Lk, Lkp;
+  long long kv_bstride, kv_hstride;        // packed K/V cache (decode): element strides per sample / head
   float scale, scale_log2;
   DropoutCfg drop;
   uint32_t drop_stream;
@@ -278,6 +280,249 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
   const int rows_valid = max(0, min(16, nq - warp * 16));
   store_rows_bf16<HD>(o_acc, 1.0f / l_run[0], 1.0f / l_run[1], Qs + (size_t)warp * 16 * kLd,
                       p.o + ((size_t)b * p.Lq + q0 + warp * 16) * p.ldo + (size_t)h * HD, p.ldo, rows_valid, lane);
+}
+
+// ================================================================================================
+// decode forward: a short query block (<= 64 rows per CTA) against a long K/V, no dropout.
+// This is the caption-decode shape (full_model.py:241-261 calls the bridge on a prefix of 1..64
+// tokens against the 257 cached vision keys of each image): the work is reading K/V once, so the
+// kernel is organised around keeping HBM requests in flight rather than around the MMA.
+//   * K/V are streamed in 16-key tiles through a 4-stage ring of TMA bulk row copies with
+//     full/empty mbarriers; a tile is refilled by the first warp of the group that consumed it one
+//     iteration earlier, so three tiles (2 x 9 KB each at d = 288) per CTA are always in flight;
+//     two CTAs are resident per SM.
+//   * warps = query row groups (16 rows) x key splits: with <= 32 query rows the idle warps take
+//     every other key tile (flash-decoding inside the CTA) and the partial (max, sum, O) are merged
+//     through the ring's shared memory at the end.
+//   * padding rows (query rows past the block, keys past the sequence) are loaded as duplicates of
+//     the last valid row, so shared memory only ever holds finite data; padded keys are masked.
+// ================================================================================================
+template <int HD>
+struct DecodeCfg {
+  static constexpr int kTile = 16;   // keys per stage
+  static constexpr int kStages = 4;
+  static constexpr int kLd = HD + 8;
+  static constexpr int kRowBytes = HD * 2;
+  static constexpr int kStageElems = 2 * kTile * kLd;  // K rows, then V rows
+  static size_t smem_bytes(int row_groups) {
+    return ((size_t)row_groups * 16 * kLd + (size_t)kStages * kStageElems) * 2;
+  }
+};
+
+template <int HD, bool PACKED>
+__global__ void __launch_bounds__(128, 2) attn_decode_kernel(const AttnParams p) {
+  using Cfg = DecodeCfg<HD>;
+  constexpr int kLd = Cfg::kLd, NS = Cfg::kStages, TK = Cfg::kTile;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64;
+  const int nq = min(64, p.Lq - q0);
+  const int nrg = (nq + 15) >> 4;       // 16-row query groups: 1..4
+  const int KS = (nrg <= 2) ? 2 : 1;    // key splits
+  const bool active = warp < nrg * KS;
+  const int rg = warp % nrg, ks = warp / nrg;
+  const int nt = (p.Lk + TK - 1) / TK;
+
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+  __nv_bfloat16* ring = Qs + (size_t)nrg * 16 * kLd;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], (uint32_t)nrg);
+    }
+    fence_barrier_init();
+  }
+  if (PACKED && nt <= NS && (p.Lk % TK) != 0) {
+    // the last tile is partial and its stage is never filled by an earlier (full) tile: the rows the
+    // copy does not write must hold finite data (their probabilities are exactly 0)
+    __nv_bfloat16* st = ring + (size_t)((nt - 1) % NS) * Cfg::kStageElems;
+    const int r0 = p.Lk % TK, nz = (TK - r0) * kLd * 2 / 16;
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) {
+      reinterpret_cast<uint4*>(st + (size_t)r0 * kLd)[i] = make_uint4(0, 0, 0, 0);
+      reinterpret_cast<uint4*>(st + (size_t)(TK + r0) * kLd)[i] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  __syncthreads();
+
+  // one warp stages key tile t
+  auto issue_tile = [&](int t) {
+    const int st = t % NS;
+    if constexpr (PACKED) {
+      // the cache holds, per (sample, head), Lk padded K rows then Lk padded V rows: a tile is two copies
+      if (lane == 0) {
+        const int nk = min(TK, p.Lk - t * TK);
+        const uint32_t bytes = (uint32_t)(nk * kLd * 2);
+        __nv_bfloat16* dst = ring + (size_t)st * Cfg::kStageElems;
+        const __nv_bfloat16* src = p.k + (size_t)b * p.kv_bstride + (size_t)h * p.kv_hstride + (size_t)t * TK * kLd;
+        mbar_arrive_expect_tx(&full_bar[st], 2 * bytes);
+        bulk_load_1d(dst, src, bytes, &full_bar[st]);
+        bulk_load_1d(dst + (size_t)TK * kLd, src + (size_t)p.Lk * kLd, bytes, &full_bar[st]);
+      }
+    } else {
+      // row-major projections: lanes 0-15 copy the tile's K rows, lanes 16-31 its V rows
+      __nv_bfloat16* dst = ring + (size_t)st * Cfg::kStageElems + (size_t)lane * kLd;
+      const size_t grow = (size_t)b * p.Lk + min(t * TK + (lane & 15), p.Lk - 1);
+      const __nv_bfloat16* src = (lane < 16) ? p.k + grow * p.ldk : p.v + grow * p.ldv;
+      if (lane == 0) mbar_arrive_expect_tx(&full_bar[st], (uint32_t)(2 * TK * Cfg::kRowBytes));
+      __syncwarp();
+      bulk_load_1d(dst, src + (size_t)h * HD, Cfg::kRowBytes, &full_bar[st]);
+    }
+  };
+
+  if (active && rg == 0)
+    for (int t = ks; t < nt && t < NS; t += KS) issue_tile(t);
+  {
+    // Q block: plain vector loads by all threads (the K/V copies above are already in flight)
+    constexpr int kChunks = HD / 8;
+    for (int idx = threadIdx.x; idx < nrg * 16 * kChunks; idx += blockDim.x) {
+      const int r = idx / kChunks, c = idx % kChunks;
+      *reinterpret_cast<uint4*>(Qs + (size_t)r * kLd + c * 8) = __ldg(reinterpret_cast<const uint4*>(
+          p.q + ((size_t)b * p.Lq + q0 + min(r, nq - 1)) * p.ldq + (size_t)h * HD + c * 8));
+    }
+  }
+  __syncthreads();
+
+  float o_acc[HD / 8][4];
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) o_acc[n][0] = o_acc[n][1] = o_acc[n][2] = o_acc[n][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const int g = lane >> 2, t4 = lane & 3;
+
+  if (active) {
+    const uint32_t a_base = smem_u32(Qs + (size_t)(rg * 16 + (lane & 15)) * kLd + (lane >> 4) * 8);
+    const uint32_t b_off = (uint32_t)((((lane & 7) + ((lane >> 4) << 3)) * kLd + ((lane >> 3) & 1) * 8) * 2);
+    for (int t = ks; t < nt; t += KS) {
+      const int st = t % NS;
+      if (rg == 0 && t >= KS && t - KS + NS < nt) {  // refill the stage this group released one iteration ago
+        const int tp = t - KS;
+        mbar_wait(&empty_bar[tp % NS], (uint32_t)((tp / NS) & 1));
+        issue_tile(tp + NS);
+      }
+      mbar_wait(&full_bar[st], (uint32_t)((t / NS) & 1));
+      if (p.Lkp < 0) {  // DEBUG: copy-only
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[st]);
+        continue;
+      }
+      const __nv_bfloat16* Kst = ring + (size_t)st * Cfg::kStageElems;
+      const __nv_bfloat16* Vst = Kst + (size_t)TK * kLd;
+
+      // S = Q K^T over the head dim; two accumulator sets halve the dependent-MMA chain
+      float s[2][4], s2[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[n][e] = s2[n][e] = 0.f;
+      const uint32_t b_base = smem_u32(Kst) + b_off;
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk) {
+        uint32_t a[4], bb[4];
+        ldmatrix_x4(a, a_base + kk * 32);
+        ldmatrix_x4(bb, b_base + kk * 32);
+        const uint32_t b0[2] = {bb[0], bb[1]}, b1[2] = {bb[2], bb[3]};
+        if (kk & 1) {
+          mma_m16n8k16(s2[0], a, b0);
+          mma_m16n8k16(s2[1], a, b1);
+        } else {
+          mma_m16n8k16(s[0], a, b0);
+          mma_m16n8k16(s[1], a, b1);
+        }
+      }
+      const int j0 = t * TK;
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = j0 + n * 8 + 2 * t4 + (e & 1);
+          s[n][e] = (col < p.Lk) ? (s[n][e] + s2[n][e]) * p.scale_log2 : -INFINITY;
+        }
+        mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m_run[0], mx0), mn1 = fmaxf(m_run[1], mx1);   // finite: every tile has a valid key
+      const float al0 = exp2f(m_run[0] - mn0), al1 = exp2f(m_run[1] - mn1);
+      m_run[0] = mn0;
+      m_run[1] = mn1;
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        s[n][0] = exp2f(s[n][0] - mn0);
+        s[n][1] = exp2f(s[n][1] - mn0);
+        s[n][2] = exp2f(s[n][2] - mn1);
+        s[n][3] = exp2f(s[n][3] - mn1);
+        rs0 += s[n][0] + s[n][1];
+        rs1 += s[n][2] + s[n][3];
+      }
+      l_run[0] = l_run[0] * al0 + rs0;
+      l_run[1] = l_run[1] * al1 + rs1;
+      if (al0 != 1.0f || al1 != 1.0f) {   // warp-divergent only in the rescale, which most tiles skip
+#pragma unroll
+        for (int n = 0; n < HD / 8; ++n) {
+          o_acc[n][0] *= al0; o_acc[n][1] *= al0;
+          o_acc[n][2] *= al1; o_acc[n][3] *= al1;
+        }
+      }
+      mma_frag_x_cols<HD, TK>(o_acc, s, Vst, lane);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[st]);
+    }
+  }
+
+  // merge the key splits through the (now idle) ring: one stage holds exactly one warp's partials
+  __syncthreads();
+  float* scratch = reinterpret_cast<float*>(ring + (size_t)rg * Cfg::kStageElems);
+  if (active && KS == 2 && ks == 1) {
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) scratch[(n * 4 + e) * 32 + lane] = o_acc[n][e];
+    scratch[(HD / 2 + 0) * 32 + lane] = m_run[0];
+    scratch[(HD / 2 + 1) * 32 + lane] = m_run[1];
+    scratch[(HD / 2 + 2) * 32 + lane] = l_run[0];
+    scratch[(HD / 2 + 3) * 32 + lane] = l_run[1];
+  }
+  __syncthreads();
+  if (!active || ks != 0) return;
+  if (KS == 2) {
+    const float mb0 = scratch[(HD / 2 + 0) * 32 + lane], mb1 = scratch[(HD / 2 + 1) * 32 + lane];
+    const float lb0 = scratch[(HD / 2 + 2) * 32 + lane], lb1 = scratch[(HD / 2 + 3) * 32 + lane];
+    const float mn0 = fmaxf(m_run[0], mb0), mn1 = fmaxf(m_run[1], mb1);
+    const float fa0 = exp2f(m_run[0] - mn0), fa1 = exp2f(m_run[1] - mn1);
+    const float fb0 = exp2f(mb0 - mn0), fb1 = exp2f(mb1 - mn1);   // 0 when the other split saw no key
+    m_run[0] = mn0;
+    m_run[1] = mn1;
+    l_run[0] = l_run[0] * fa0 + lb0 * fb0;
+    l_run[1] = l_run[1] * fa1 + lb1 * fb1;
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n) {
+      o_acc[n][0] = o_acc[n][0] * fa0 + scratch[(n * 4 + 0) * 32 + lane] * fb0;
+      o_acc[n][1] = o_acc[n][1] * fa0 + scratch[(n * 4 + 1) * 32 + lane] * fb0;
+      o_acc[n][2] = o_acc[n][2] * fa1 + scratch[(n * 4 + 2) * 32 + lane] * fb1;
+      o_acc[n][3] = o_acc[n][3] * fa1 + scratch[(n * 4 + 3) * 32 + lane] * fb1;
+    }
+  }
+  l_run[0] += __shfl_xor_sync(0xffffffffu, l_run[0], 1);
+  l_run[0] += __shfl_xor_sync(0xffffffffu, l_run[0], 2);
+  l_run[1] += __shfl_xor_sync(0xffffffffu, l_run[1], 1);
+  l_run[1] += __shfl_xor_sync(0xffffffffu, l_run[1], 2);
+  const int row0 = q0 + rg * 16 + g;
+  if (t4 == 0 && p.lse2 != nullptr) {
+    const size_t bh = (size_t)b * p.H + h;
+    if (row0 < p.Lq) p.lse2[bh * p.Lq + row0] = m_run[0] + log2f(l_run[0]);
+    if (row0 + 8 < p.Lq) p.lse2[bh * p.Lq + row0 + 8] = m_run[1] + log2f(l_run[1]);
+  }
+  const int rows_valid = max(0, min(16, nq - rg * 16));
+  store_rows_bf16<HD>(o_acc, 1.0f / l_run[0], 1.0f / l_run[1], Qs + (size_t)rg * 16 * kLd,
+                      p.o + ((size_t)b * p.Lq + q0 + rg * 16) * p.ldo + (size_t)h * HD, p.ldo, rows_valid, lane);
 }
 
 // ================================================================================================
@@ -545,6 +790,28 @@ static int launch_fwd(const AttnParams& p, cudaStream_t stream) {
   return check_launch("attn_fwd", stream);
 }
 
+// Short query blocks without dropout (caption decode, and any inference call on <= 64 tokens) take
+// the K/V-streaming kernel.
+static bool use_decode_kernel(const AttnParams& p) { return p.drop.thr == 0 && p.Lq <= 64; }
+
+template <int HD, bool PACKED>
+static int launch_decode(const AttnParams& p, cudaStream_t stream) {
+  using Cfg = DecodeCfg<HD>;
+  static bool attr_done = false;  // the maximum is the same for every launch; a race only repeats the call
+  if (!attr_done) {
+    int rc = set_smem(attn_decode_kernel<HD, PACKED>, Cfg::smem_bytes(4), "attn_decode");
+    if (rc) return rc;
+    attr_done = true;
+  }
+  const int nrg = (min(64, p.Lq) + 15) / 16;
+  dim3 grid((p.Lq + 63) / 64, p.H, p.B);
+  static const int dbg = [] { const char* e = getenv("B200B_DECODE_DEBUG"); return e ? atoi(e) : 0; }();
+  AttnParams pp = p;
+  if (dbg & 1) pp.Lkp = -1;
+  attn_decode_kernel<HD, PACKED><<<grid, 128, Cfg::smem_bytes(nrg), stream>>>(pp);
+  return check_launch(PACKED ? "attn_decode_packed" : "attn_decode", stream);
+}
+
 template <int HD>
 static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
   using Cfg = AttnCfg<HD>;
@@ -618,6 +885,13 @@ extern "C" int b200b_attention_fwd(const b200b_attn_args* a, void* stream_) {
   int rc = validate_common(a, "attention_fwd");
   if (rc) return rc;
   AttnParams p = make_params(a);
+  if (use_decode_kernel(p)) {
+    switch (a->head_dim) {
+      case 64: return launch_decode<64, false>(p, stream);
+      case 128: return launch_decode<128, false>(p, stream);
+      default: return launch_decode<288, false>(p, stream);
+    }
+  }
   switch (a->head_dim) {
     case 64: return launch_fwd<64>(p, stream);
     case 128: return launch_fwd<128>(p, stream);
@@ -666,5 +940,93 @@ extern "C" int b200b_attention_bwd(const b200b_attn_args* a, void* stream_) {
     case 64: return launch_bwd<64>(p, stream);
     case 128: return launch_bwd<128>(p, stream);
     default: return launch_bwd<288>(p, stream);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// packed K/V cache for decode
+// ------------------------------------------------------------------------------------------------
+namespace b200b {
+
+// kv [B*Lk, nb*2*H*HD] (block i: K columns then V columns) -> packed [B][nb][H][2][Lk][HD+8]: per
+// (sample, block, head) the K rows and then the V rows, each padded to the shared-memory row pitch of
+// the decode kernel, so that a 16-key tile is ONE contiguous copy that lands bank-conflict free.
+__global__ void kv_cache_pack_kernel(const __nv_bfloat16* __restrict__ kv, long long ldkv,
+                                     __nv_bfloat16* __restrict__ packed, int B, int Lk, int H, int HD, int nb) {
+  const int chunks = (HD + 8) / 8;  // 16-byte chunks per padded row
+  const long long total = (long long)B * nb * H * 2 * Lk * chunks;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % chunks);
+    long long r = i / chunks;
+    const int j = (int)(r % Lk); r /= Lk;
+    const int which = (int)(r % 2); r /= 2;
+    const int h = (int)(r % H); r /= H;
+    const int blk = (int)(r % nb);
+    const int b = (int)(r / nb);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (c * 8 < HD)
+      v = __ldg(reinterpret_cast<const uint4*>(kv + ((long long)b * Lk + j) * ldkv + (long long)(2 * blk + which) * H * HD +
+                                               (long long)h * HD + c * 8));
+    reinterpret_cast<uint4*>(packed)[i] = v;
+  }
+}
+
+}  // namespace b200b
+
+extern "C" size_t b200b_kv_cache_packed_bytes(int batch, int len_k, int heads, int head_dim, int num_blocks) {
+  return (size_t)batch * num_blocks * heads * 2 * len_k * (head_dim + 8) * 2;
+}
+
+extern "C" int b200b_kv_cache_pack(const void* kv, int64_t ldkv, void* packed, int batch, int len_k, int heads,
+                                   int head_dim, int num_blocks, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!kv || !packed || batch <= 0 || len_k <= 0 || heads <= 0 || num_blocks <= 0 || head_dim <= 0 || (head_dim % 8) ||
+      (ldkv % 8) || !al16p(kv) || !al16p(packed)) {
+    set_last_error("kv_cache_pack: bad argument (need 16-byte aligned pointers, head_dim and ldkv multiples of 8)");
+    return B200B_ERR_ARG;
+  }
+  const long long total = (long long)batch * num_blocks * heads * 2 * len_k * ((head_dim + 8) / 8);
+  const int threads = 256;
+  const int blocks = (int)((total + threads - 1) / threads < 148 * 16 ? (total + threads - 1) / threads : 148 * 16);
+  kv_cache_pack_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(kv), ldkv,
+                                                       reinterpret_cast<__nv_bfloat16*>(packed), batch, len_k, heads,
+                                                       head_dim, num_blocks);
+  return check_launch("kv_cache_pack", stream);
+}
+
+extern "C" int b200b_attention_decode_packed(const void* q, int64_t ldq, const void* kv_packed, int block_index,
+                                             int num_blocks, void* o, int64_t ldo, float* lse, int batch, int heads,
+                                             int len_q, int len_k, int head_dim, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!q || !kv_packed || !o || batch <= 0 || heads <= 0 || len_q <= 0 || len_q > 64 || len_k <= 0 ||
+      block_index < 0 || block_index >= num_blocks) {
+    set_last_error("attention_decode_packed: bad argument (need 1 <= len_q <= 64, 0 <= block_index < num_blocks)");
+    return B200B_ERR_ARG;
+  }
+  if (head_dim != 64 && head_dim != 128 && head_dim != 288) {
+    set_last_error("attention_decode_packed: head_dim %d not built (64, 128, 288)", head_dim);
+    return B200B_ERR_SHAPE;
+  }
+  if (!al16p(q) || !al16p(kv_packed) || !al16p(o) || (ldq % 8) || (ldo % 8)) {
+    set_last_error("attention_decode_packed: q/kv/o must be 16-byte aligned with row pitch multiple of 8 elements");
+    return B200B_ERR_ALIGN;
+  }
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  const long long per_head = 2LL * len_k * (head_dim + 8);
+  p.q = reinterpret_cast<const __nv_bfloat16*>(q); p.ldq = ldq;
+  p.k = reinterpret_cast<const __nv_bfloat16*>(kv_packed) + (long long)block_index * heads * per_head;
+  p.kv_hstride = per_head;
+  p.kv_bstride = (long long)num_blocks * heads * per_head;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o); p.ldo = ldo;
+  p.lse2 = lse;
+  p.B = batch; p.H = heads; p.Lq = len_q; p.Lk = len_k; p.Lkp = (len_k + 7) & ~7;
+  p.scale = 1.0f / sqrtf((float)head_dim);
+  p.scale_log2 = p.scale * 1.4426950408889634f;
+  p.drop = make_dropout_cfg(0.f, 0, nullptr);
+  switch (head_dim) {
+    case 64: return launch_decode<64, true>(p, stream);
+    case 128: return launch_decode<128, true>(p, stream);
+    default: return launch_decode<288, true>(p, stream);
   }
 }

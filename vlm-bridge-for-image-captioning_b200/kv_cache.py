@@ -6,9 +6,11 @@ prefix and re-projects the unchanged image through w_k / w_v of every block
 bridge self-attention is non-causal and unmasked (:138,236) the text side cannot be cached exactly,
 but the vision K/V can: they are computed once per image here and every decode step reads them.
 
-The cache is a plain torch tensor (bf16, [B*Nv, num_blocks*2*D]; block i's K at columns
-[2iD, 2iD+D), V in the next D columns) owned by this object; the CUDA library only ever sees its
-pointer for the duration of a call.
+The cache is two plain torch tensors owned by this object: `kv` (bf16, [B*Nv, num_blocks*2*D]; block
+i's K at columns [2iD, 2iD+D), V in the next D columns -- the projection output, used for steps of more
+than 64 positions) and `kv_packed` (the same values as [B][num_blocks][heads][2][Nv][d+8], the layout
+the decode kernel streams with one bulk copy per 16-key tile). The CUDA library only ever sees their
+pointers for the duration of a call.
 """
 from __future__ import annotations
 
@@ -24,12 +26,16 @@ class VisionKVCache:
         self.batch, self.len_vision = int(vision_features.shape[0]), int(vision_features.shape[1])
         with torch.no_grad():
             self.vision_bf16, self.kv = bridge.project_vision_kv(vision_features)
+            # decode layout (per image / block / head: padded K rows then V rows), read by the K/V-streaming
+            # cross-attention kernel whenever a step has <= 64 text positions
+            self.kv_packed = bridge.pack_vision_kv(self.kv, self.batch, self.len_vision)
         self._versions = tuple(p._version for p in bridge.parameters())
         self._bridge = bridge
 
     @property
     def nbytes(self) -> int:
-        return self.kv.numel() * self.kv.element_size()
+        """bytes of the decode-layout cache (what a decode step reads)"""
+        return self.kv_packed.numel() * self.kv_packed.element_size()
 
     def is_current(self) -> bool:
         """False once the bridge weights were updated after the cache was filled."""

@@ -227,3 +227,28 @@ def attention_bwd(d_o: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.
     args.dv, args.lddv = dv.data_ptr(), dv.stride(0)
     args.workspace, args.workspace_bytes = workspace.data_ptr(), workspace.numel()
     _lib.check(_lib.lib().b200b_attention_bwd(C.byref(args), _stream_ptr()), "attention_bwd")
+
+
+def kv_cache_pack(kv: torch.Tensor, *, batch: int, len_k: int, heads: int, head_dim: int,
+                  num_blocks: int) -> torch.Tensor:
+    """kv bf16 [batch*len_k, num_blocks*2*heads*head_dim] -> decode layout (flat uint8 tensor)."""
+    _need_cuda(kv)
+    nbytes = _lib.lib().b200b_kv_cache_packed_bytes(batch, len_k, heads, head_dim, num_blocks)
+    packed = torch.empty(nbytes, device=kv.device, dtype=torch.uint8)
+    _lib.check(_lib.lib().b200b_kv_cache_pack(kv.data_ptr(), kv.stride(0), packed.data_ptr(), batch, len_k, heads,
+                                              head_dim, num_blocks, _stream_ptr()), "kv_cache_pack")
+    return packed
+
+
+def attention_decode_packed(q: torch.Tensor, kv_packed: torch.Tensor, *, block_index: int, num_blocks: int,
+                            batch: int, heads: int, len_q: int, len_k: int, head_dim: int,
+                            out: torch.Tensor | None = None, want_lse: bool = True):
+    """Cross-attention of <= 64 query rows per image against block `block_index` of a packed K/V cache."""
+    _need_cuda(q, kv_packed, out)
+    if out is None:
+        out = torch.empty((batch * len_q, heads * head_dim), device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty((batch, heads, len_q), device=q.device, dtype=torch.float32) if want_lse else None
+    _lib.check(_lib.lib().b200b_attention_decode_packed(
+        q.data_ptr(), q.stride(0), kv_packed.data_ptr(), block_index, num_blocks, out.data_ptr(), out.stride(0),
+        _ptr(lse), batch, heads, len_q, len_k, head_dim, _stream_ptr()), "attention_decode_packed")
+    return out, lse
