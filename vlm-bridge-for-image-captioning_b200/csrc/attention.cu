@@ -286,53 +286,66 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
 // decode forward: a short query block (<= 64 rows per CTA) against a long K/V, no dropout.
 // This is the caption-decode shape (full_model.py:241-261 calls the bridge on a prefix of 1..64
 // tokens against the 257 cached vision keys of each image): the work is reading K/V once, so the
-// kernel is organised around keeping HBM requests in flight rather than around the MMA.
-//   * K/V are streamed in 16-key tiles through a 4-stage ring of TMA bulk row copies with
-//     full/empty mbarriers; a tile is refilled by the first warp of the group that consumed it one
-//     iteration earlier, so three tiles (2 x 9 KB each at d = 288) per CTA are always in flight;
-//     two CTAs are resident per SM.
-//   * warps = query row groups (16 rows) x key splits: with <= 32 query rows the idle warps take
-//     every other key tile (flash-decoding inside the CTA) and the partial (max, sum, O) are merged
-//     through the ring's shared memory at the end.
-//   * padding rows (query rows past the block, keys past the sequence) are loaded as duplicates of
-//     the last valid row, so shared memory only ever holds finite data; padded keys are masked.
+// kernel is organised around keeping HBM requests in flight and enough warps resident to hide the
+// latency of the (legacy-path) mma.sync chains.
+//   * K/V are streamed in 16-key tiles through a 3/4-stage ring of TMA bulk copies with full/empty
+//     mbarriers; a stage is refilled by the first warp of the group that consumed it one iteration
+//     earlier. With the packed cache layout (b200b_kv_cache_pack) a tile is two 9 KB copies.
+//   * a PAIR of warps owns 16 query rows: each computes Q K^T over half of the head dim, the two
+//     partial score tiles are exchanged through shared memory (one named barrier per tile), both
+//     run the same online softmax, and each accumulates P V for half of the output columns. That
+//     halves the accumulator registers, so 16 warps (2 CTAs of 8) are resident per SM.
+//   * with <= 32 query rows the spare pairs take every other key tile (flash-decoding inside the
+//     CTA); the partial (max, sum, O) are merged through the ring's shared memory at the end.
+//   * padding rows are duplicates of the last valid row (or zeros), so shared memory only ever
+//     holds finite data; padded keys are masked to -inf.
 // ================================================================================================
 template <int HD>
 struct DecodeCfg {
   static constexpr int kTile = 16;   // keys per stage
-  static constexpr int kStages = 4;
   static constexpr int kLd = HD + 8;
   static constexpr int kRowBytes = HD * 2;
   static constexpr int kStageElems = 2 * kTile * kLd;  // K rows, then V rows
+  static constexpr int kXchgBytes = 4 * 2 * 2 * 8 * 32 * 4;  // [pair][tile parity][half][8 floats][lane]
+  static int stages(int row_groups) { return row_groups >= 3 ? 3 : 4; }
   static size_t smem_bytes(int row_groups) {
-    return ((size_t)row_groups * 16 * kLd + (size_t)kStages * kStageElems) * 2;
+    return ((size_t)row_groups * 16 * kLd + (size_t)stages(row_groups) * kStageElems) * 2 + kXchgBytes;
   }
 };
 
+__device__ __forceinline__ void pair_barrier(int pair) {
+  asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+}
+
 template <int HD, bool PACKED>
-__global__ void __launch_bounds__(128, 2) attn_decode_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(256, 2) attn_decode_kernel(const AttnParams p) {
   using Cfg = DecodeCfg<HD>;
-  constexpr int kLd = Cfg::kLd, NS = Cfg::kStages, TK = Cfg::kTile;
+  constexpr int kLd = Cfg::kLd, TK = Cfg::kTile;
+  constexpr int KH = HD / 32;    // 16-wide k-steps of Q K^T per warp (half of the head dim)
+  constexpr int NH = HD / 16;    // 8-column accumulator tiles per warp (half of the output columns)
+  constexpr int kMaxStages = 4;
   extern __shared__ __align__(16) uint8_t smem_attn[];
-  __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = warp >> 1, half = warp & 1;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64;
   const int nq = min(64, p.Lq - q0);
   const int nrg = (nq + 15) >> 4;       // 16-row query groups: 1..4
   const int KS = (nrg <= 2) ? 2 : 1;    // key splits
-  const bool active = warp < nrg * KS;
-  const int rg = warp % nrg, ks = warp / nrg;
+  const int NS = (nrg >= 3) ? 3 : 4;    // ring stages (a multiple of KS)
+  const bool active = pair < nrg * KS;
+  const int rg = pair % nrg, ks = pair / nrg;
   const int nt = (p.Lk + TK - 1) / TK;
 
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_attn);
   __nv_bfloat16* ring = Qs + (size_t)nrg * 16 * kLd;
+  float4* xchg = reinterpret_cast<float4*>(ring + (size_t)NS * Cfg::kStageElems) + (size_t)pair * (2 * 2 * 2 * 32);
 
   if (threadIdx.x == 0) {
-#pragma unroll
     for (int s = 0; s < NS; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], (uint32_t)nrg);
+      mbar_init(&empty_bar[s], (uint32_t)(2 * nrg));
     }
     fence_barrier_init();
   }
@@ -372,8 +385,9 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(const AttnParams p)
       bulk_load_1d(dst, src + (size_t)h * HD, Cfg::kRowBytes, &full_bar[st]);
     }
   };
+  const bool refiller = active && rg == 0 && half == 0;
 
-  if (active && rg == 0)
+  if (refiller)
     for (int t = ks; t < nt && t < NS; t += KS) issue_tile(t);
   {
     // Q block: plain vector loads by all threads (the K/V copies above are already in flight)
@@ -386,43 +400,46 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(const AttnParams p)
   }
   __syncthreads();
 
-  float o_acc[HD / 8][4];
+  float o_acc[NH][4];
 #pragma unroll
-  for (int n = 0; n < HD / 8; ++n) o_acc[n][0] = o_acc[n][1] = o_acc[n][2] = o_acc[n][3] = 0.f;
+  for (int n = 0; n < NH; ++n) o_acc[n][0] = o_acc[n][1] = o_acc[n][2] = o_acc[n][3] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   const int g = lane >> 2, t4 = lane & 3;
 
   if (active) {
-    const uint32_t a_base = smem_u32(Qs + (size_t)(rg * 16 + (lane & 15)) * kLd + (lane >> 4) * 8);
-    const uint32_t b_off = (uint32_t)((((lane & 7) + ((lane >> 4) << 3)) * kLd + ((lane >> 3) & 1) * 8) * 2);
-    for (int t = ks; t < nt; t += KS) {
+    // Q K^T: this warp's half of the head dim; P V: this warp's half of the output columns
+    const uint32_t a_base = smem_u32(Qs + (size_t)(rg * 16 + (lane & 15)) * kLd + (lane >> 4) * 8 + half * (HD / 2));
+    const uint32_t b_off =
+        (uint32_t)((((lane & 7) + ((lane >> 4) << 3)) * kLd + ((lane >> 3) & 1) * 8 + half * (HD / 2)) * 2);
+    const uint32_t v_off =
+        (uint32_t)(((TK + (lane & 7) + ((lane >> 3) & 1) * 8) * kLd + (lane >> 4) * 8 + half * (HD / 2)) * 2);
+    int it = 0;
+    for (int t = ks; t < nt; t += KS, ++it) {
       const int st = t % NS;
-      if (rg == 0 && t >= KS && t - KS + NS < nt) {  // refill the stage this group released one iteration ago
+      if (refiller && t >= KS && t - KS + NS < nt) {  // refill the stage this group released one iteration ago
         const int tp = t - KS;
         mbar_wait(&empty_bar[tp % NS], (uint32_t)((tp / NS) & 1));
         issue_tile(tp + NS);
       }
       mbar_wait(&full_bar[st], (uint32_t)((t / NS) & 1));
-      if (p.Lkp < 0) {  // DEBUG: copy-only
+      const uint32_t st_base = smem_u32(ring + (size_t)st * Cfg::kStageElems);
+      if (p.Lkp < 0) {  // DEBUG (B200B_DECODE_DEBUG=1): copy-only
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[st]);
         continue;
       }
-      const __nv_bfloat16* Kst = ring + (size_t)st * Cfg::kStageElems;
-      const __nv_bfloat16* Vst = Kst + (size_t)TK * kLd;
 
-      // S = Q K^T over the head dim; two accumulator sets halve the dependent-MMA chain
+      // partial S = Q[:, half] K[:, half]^T; two accumulator sets shorten the dependent-MMA chains
       float s[2][4], s2[2][4];
 #pragma unroll
       for (int n = 0; n < 2; ++n)
 #pragma unroll
         for (int e = 0; e < 4; ++e) s[n][e] = s2[n][e] = 0.f;
-      const uint32_t b_base = smem_u32(Kst) + b_off;
 #pragma unroll
-      for (int kk = 0; kk < HD / 16; ++kk) {
+      for (int kk = 0; kk < KH; ++kk) {
         uint32_t a[4], bb[4];
         ldmatrix_x4(a, a_base + kk * 32);
-        ldmatrix_x4(bb, b_base + kk * 32);
+        ldmatrix_x4(bb, st_base + b_off + kk * 32);
         const uint32_t b0[2] = {bb[0], bb[1]}, b1[2] = {bb[2], bb[3]};
         if (kk & 1) {
           mma_m16n8k16(s2[0], a, b0);
@@ -432,6 +449,18 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(const AttnParams p)
           mma_m16n8k16(s[1], a, b1);
         }
       }
+      // exchange with the other warp of the pair (a + b == b + a exactly: both end with the same S)
+      float4* mine = xchg + ((it & 1) * 2 + half) * 64;
+      const float4* other = xchg + ((it & 1) * 2 + (half ^ 1)) * 64;
+      mine[lane] = make_float4(s[0][0] + s2[0][0], s[0][1] + s2[0][1], s[0][2] + s2[0][2], s[0][3] + s2[0][3]);
+      mine[32 + lane] = make_float4(s[1][0] + s2[1][0], s[1][1] + s2[1][1], s[1][2] + s2[1][2], s[1][3] + s2[1][3]);
+      pair_barrier(pair);
+      {
+        const float4 o0 = other[lane], o1 = other[32 + lane];
+        const float4 m0 = mine[lane], m1 = mine[32 + lane];
+        s[0][0] = m0.x + o0.x; s[0][1] = m0.y + o0.y; s[0][2] = m0.z + o0.z; s[0][3] = m0.w + o0.w;
+        s[1][0] = m1.x + o1.x; s[1][1] = m1.y + o1.y; s[1][2] = m1.z + o1.z; s[1][3] = m1.w + o1.w;
+      }
       const int j0 = t * TK;
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -439,7 +468,7 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(const AttnParams p)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int col = j0 + n * 8 + 2 * t4 + (e & 1);
-          s[n][e] = (col < p.Lk) ? (s[n][e] + s2[n][e]) * p.scale_log2 : -INFINITY;
+          s[n][e] = (col < p.Lk) ? s[n][e] * p.scale_log2 : -INFINITY;
         }
         mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
         mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
@@ -464,37 +493,52 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(const AttnParams p)
       }
       l_run[0] = l_run[0] * al0 + rs0;
       l_run[1] = l_run[1] * al1 + rs1;
-      if (al0 != 1.0f || al1 != 1.0f) {   // warp-divergent only in the rescale, which most tiles skip
+      if (al0 != 1.0f || al1 != 1.0f) {   // the running maximum settles after a few tiles
 #pragma unroll
-        for (int n = 0; n < HD / 8; ++n) {
+        for (int n = 0; n < NH; ++n) {
           o_acc[n][0] *= al0; o_acc[n][1] *= al0;
           o_acc[n][2] *= al1; o_acc[n][3] *= al1;
         }
       }
-      mma_frag_x_cols<HD, TK>(o_acc, s, Vst, lane);
+      {
+        uint32_t a[4];
+        a[0] = pack_bf16(s[0][0], s[0][1]);
+        a[1] = pack_bf16(s[0][2], s[0][3]);
+        a[2] = pack_bf16(s[1][0], s[1][1]);
+        a[3] = pack_bf16(s[1][2], s[1][3]);
+#pragma unroll
+        for (int dp = 0; dp < NH / 2; ++dp) {
+          uint32_t bb[4];
+          ldmatrix_x4_trans(bb, st_base + v_off + dp * 32);
+          const uint32_t b0[2] = {bb[0], bb[1]}, b1[2] = {bb[2], bb[3]};
+          mma_m16n8k16(o_acc[2 * dp], a, b0);
+          mma_m16n8k16(o_acc[2 * dp + 1], a, b1);
+        }
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[st]);
     }
   }
 
-  // merge the key splits through the (now idle) ring: one stage holds exactly one warp's partials
+  // merge the key splits through the (now idle) ring
   __syncthreads();
-  float* scratch = reinterpret_cast<float*>(ring + (size_t)rg * Cfg::kStageElems);
+  constexpr int kSlotFloats = (NH * 4 + 4) * 32;
+  float* scratch = reinterpret_cast<float*>(ring) + (size_t)(rg * 2 + half) * kSlotFloats;
   if (active && KS == 2 && ks == 1) {
 #pragma unroll
-    for (int n = 0; n < HD / 8; ++n)
+    for (int n = 0; n < NH; ++n)
 #pragma unroll
       for (int e = 0; e < 4; ++e) scratch[(n * 4 + e) * 32 + lane] = o_acc[n][e];
-    scratch[(HD / 2 + 0) * 32 + lane] = m_run[0];
-    scratch[(HD / 2 + 1) * 32 + lane] = m_run[1];
-    scratch[(HD / 2 + 2) * 32 + lane] = l_run[0];
-    scratch[(HD / 2 + 3) * 32 + lane] = l_run[1];
+    scratch[(NH * 4 + 0) * 32 + lane] = m_run[0];
+    scratch[(NH * 4 + 1) * 32 + lane] = m_run[1];
+    scratch[(NH * 4 + 2) * 32 + lane] = l_run[0];
+    scratch[(NH * 4 + 3) * 32 + lane] = l_run[1];
   }
   __syncthreads();
   if (!active || ks != 0) return;
   if (KS == 2) {
-    const float mb0 = scratch[(HD / 2 + 0) * 32 + lane], mb1 = scratch[(HD / 2 + 1) * 32 + lane];
-    const float lb0 = scratch[(HD / 2 + 2) * 32 + lane], lb1 = scratch[(HD / 2 + 3) * 32 + lane];
+    const float mb0 = scratch[(NH * 4 + 0) * 32 + lane], mb1 = scratch[(NH * 4 + 1) * 32 + lane];
+    const float lb0 = scratch[(NH * 4 + 2) * 32 + lane], lb1 = scratch[(NH * 4 + 3) * 32 + lane];
     const float mn0 = fmaxf(m_run[0], mb0), mn1 = fmaxf(m_run[1], mb1);
     const float fa0 = exp2f(m_run[0] - mn0), fa1 = exp2f(m_run[1] - mn1);
     const float fb0 = exp2f(mb0 - mn0), fb1 = exp2f(mb1 - mn1);   // 0 when the other split saw no key
@@ -503,7 +547,7 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(const AttnParams p)
     l_run[0] = l_run[0] * fa0 + lb0 * fb0;
     l_run[1] = l_run[1] * fa1 + lb1 * fb1;
 #pragma unroll
-    for (int n = 0; n < HD / 8; ++n) {
+    for (int n = 0; n < NH; ++n) {
       o_acc[n][0] = o_acc[n][0] * fa0 + scratch[(n * 4 + 0) * 32 + lane] * fb0;
       o_acc[n][1] = o_acc[n][1] * fa0 + scratch[(n * 4 + 1) * 32 + lane] * fb0;
       o_acc[n][2] = o_acc[n][2] * fa1 + scratch[(n * 4 + 2) * 32 + lane] * fb1;
@@ -515,14 +559,31 @@ __global__ void __launch_bounds__(128, 2) attn_decode_kernel(const AttnParams p)
   l_run[1] += __shfl_xor_sync(0xffffffffu, l_run[1], 1);
   l_run[1] += __shfl_xor_sync(0xffffffffu, l_run[1], 2);
   const int row0 = q0 + rg * 16 + g;
-  if (t4 == 0 && p.lse2 != nullptr) {
+  if (half == 0 && t4 == 0 && p.lse2 != nullptr) {
     const size_t bh = (size_t)b * p.H + h;
     if (row0 < p.Lq) p.lse2[bh * p.Lq + row0] = m_run[0] + log2f(l_run[0]);
     if (row0 + 8 < p.Lq) p.lse2[bh * p.Lq + row0 + 8] = m_run[1] + log2f(l_run[1]);
   }
-  const int rows_valid = max(0, min(16, nq - rg * 16));
-  store_rows_bf16<HD>(o_acc, 1.0f / l_run[0], 1.0f / l_run[1], Qs + (size_t)rg * 16 * kLd,
-                      p.o + ((size_t)b * p.Lq + q0 + rg * 16) * p.ldo + (size_t)h * HD, p.ldo, rows_valid, lane);
+  // this warp's 16 x HD/2 block: bf16 through its columns of the (idle) Q rows, then 16-byte row stores
+  {
+    const float s0 = 1.0f / l_run[0], s1 = 1.0f / l_run[1];
+    __nv_bfloat16* stage = Qs + (size_t)rg * 16 * kLd + half * (HD / 2);
+#pragma unroll
+    for (int n = 0; n < NH; ++n) {
+      *reinterpret_cast<uint32_t*>(stage + (size_t)g * kLd + n * 8 + 2 * t4) = pack_bf16(o_acc[n][0] * s0, o_acc[n][1] * s0);
+      *reinterpret_cast<uint32_t*>(stage + (size_t)(g + 8) * kLd + n * 8 + 2 * t4) =
+          pack_bf16(o_acc[n][2] * s1, o_acc[n][3] * s1);
+    }
+    __syncwarp();
+    const int rows_valid = max(0, min(16, nq - rg * 16));
+    constexpr int kChunks = HD / 16;  // 16-byte chunks per half row
+    __nv_bfloat16* gdst = p.o + ((size_t)b * p.Lq + q0 + rg * 16) * p.ldo + (size_t)h * HD + half * (HD / 2);
+    for (int idx = lane; idx < 16 * kChunks; idx += 32) {
+      const int r = idx / kChunks, c = idx % kChunks;
+      if (r < rows_valid)
+        *reinterpret_cast<uint4*>(gdst + (size_t)r * p.ldo + c * 8) = *reinterpret_cast<const uint4*>(stage + (size_t)r * kLd + c * 8);
+    }
+  }
 }
 
 // ================================================================================================
@@ -799,7 +860,7 @@ static int launch_decode(const AttnParams& p, cudaStream_t stream) {
   using Cfg = DecodeCfg<HD>;
   static bool attr_done = false;  // the maximum is the same for every launch; a race only repeats the call
   if (!attr_done) {
-    int rc = set_smem(attn_decode_kernel<HD, PACKED>, Cfg::smem_bytes(4), "attn_decode");
+    int rc = set_smem(attn_decode_kernel<HD, PACKED>, Cfg::smem_bytes(2), "attn_decode");
     if (rc) return rc;
     attr_done = true;
   }
@@ -808,7 +869,7 @@ static int launch_decode(const AttnParams& p, cudaStream_t stream) {
   static const int dbg = [] { const char* e = getenv("B200B_DECODE_DEBUG"); return e ? atoi(e) : 0; }();
   AttnParams pp = p;
   if (dbg & 1) pp.Lkp = -1;
-  attn_decode_kernel<HD, PACKED><<<grid, 128, Cfg::smem_bytes(nrg), stream>>>(pp);
+  attn_decode_kernel<HD, PACKED><<<grid, 256, Cfg::smem_bytes(nrg), stream>>>(pp);
   return check_launch(PACKED ? "attn_decode_packed" : "attn_decode", stream);
 }
 
