@@ -242,7 +242,9 @@ def run_b200_arm(args) -> int:
             model(vision_d, text_d)  # flattens parameters
         broadcast_parameters(model)
         enable_data_parallel(model, grad_dtype=torch.float32 if args.grad_dtype == "f32" else torch.bfloat16,
-                             backend=args.dp_backend, nvls_blocks=args.nvls_blocks, nvls_threads=args.nvls_threads, bucket_bytes=args.bucket_mb << 20)
+                             backend=args.dp_backend, nvls_blocks=args.nvls_blocks, nvls_threads=args.nvls_threads,
+                             bucket_bytes=args.bucket_mb << 20, exclusive_sms=args.nvls_exclusive,
+                             fp32_multicast=args.nvls_fp32_multicast)
 
     def step(v, t):
         model._w16_key = None            # weights count as updated by the optimizer since last step
@@ -505,8 +507,10 @@ def main() -> int:
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--dp-backend", default="auto", choices=["auto", "nvls", "nccl"],
                     help="transport of the gradient exchange: own NVLS multimem kernel, or NCCL")
-    ap.add_argument("--nvls-blocks", type=int, default=148)
-    ap.add_argument("--nvls-threads", type=int, default=128)
+    ap.add_argument("--nvls-blocks", type=int, default=32)
+    ap.add_argument("--nvls-threads", type=int, default=512)
+    ap.add_argument("--nvls-exclusive", action="store_true", help="reserve --nvls-blocks SMs for the exchange")
+    ap.add_argument("--nvls-fp32-multicast", action="store_true", help="broadcast fp32 into .grad (no conversion pass)")
     ap.add_argument("--bucket-mb", type=int, default=32)
     ap.add_argument("--grad-dtype", default="bf16", choices=["bf16", "f32"],
                     help="dtype of the data-parallel weight-gradient exchange (N > 1)")

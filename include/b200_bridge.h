@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200B_ABI_VERSION 1
+#define B200B_ABI_VERSION 2
 
 /* error codes (negative returns) */
 #define B200B_OK 0
@@ -350,10 +350,26 @@ typedef struct b200b_nvls_comm {
   void* flags[B200B_NVLS_MAX_RANKS];    /* flag array of rank q as mapped in this process */
   int32_t rank, world;
 } b200b_nvls_comm;
+/* flags of b200b_allreduce_nvls */
+/* out_f32 is the MULTICAST address of a second symmetric buffer (same offset on every rank, e.g. the
+ * fp32 .grad arena): the reduced bf16 slice is broadcast there as fp32 and the bf16 source is left
+ * untouched -- no in-place result, no separate bf16 -> fp32 pass. bytes % 8 == 0 is enough. */
+#define B200B_NVLS_OUT_MULTICAST 1u
+/* launch the grid as CTA pairs (clusters of two = one TPC) that claim all shared memory of their SMs,
+ * so no compute CTA is co-resident with the exchange; `blocks` must be even. Use together with
+ * b200b_set_sm_limit(SMs - blocks) on the compute side. */
+#define B200B_NVLS_EXCLUSIVE_SMS 2u
 size_t b200b_allreduce_nvls_flag_bytes(void);
 int b200b_allreduce_nvls(const b200b_nvls_comm* comm, int dtype, int64_t byte_offset, int64_t bytes,
                          float scale, float* out_f32, uint32_t epoch, const uint32_t* epoch_base,
-                         int blocks, int threads, void* stream);
+                         int blocks, int threads, uint32_t flags, void* stream);
+
+/* Number of SMs the persistent compute kernels of this library (the tcgen05 GEMMs) may occupy on the
+ * calling thread's current device: min(limit, SMs of the device); 0 or negative removes the limit.
+ * The data-parallel path lowers it by the SMs it reserves for the gradient exchange, so that the
+ * statically scheduled GEMM CTAs never share (or wait for) an SM with an exchange CTA. Process-wide. */
+void b200b_set_sm_limit(int sms);
+int b200b_get_sm_limit(void);
 
 #ifdef __cplusplus
 }

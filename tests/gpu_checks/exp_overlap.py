@@ -1,6 +1,6 @@
 """Diagnostic (torchrun, 2+ ranks): how much does a concurrent gradient exchange slow the compute
-kernels, and which part of it does? A fixed compute loop (GEMMs, or an HBM-bound cast) is timed on the
-compute stream while variants of communication work run on a side stream."""
+kernels? A fixed compute loop (the FFN forward + weight-gradient GEMM pair, or an HBM-bound cast) is
+timed on the compute stream while variants of the exchange run on a high-priority side stream."""
 import datetime
 import json
 import os
@@ -19,28 +19,30 @@ from vlm_bridge_b200.parallel import GradBucketReducer
 
 n = 64 << 20  # bf16 elements (128 MiB)
 red = GradBucketReducer(backend="nvls", grad_dtype=torch.bfloat16)
-arena16 = red.weight_arena(n, 1 << 16, dev)
-arena32 = torch.empty(n, device=dev, dtype=torch.float32)
+arena32, arena16 = red.arenas(n, n + 4096, dev)
+nv = red._nvls
 plain16 = torch.ones(n, device=dev, dtype=torch.bfloat16)
 arena16.fill_(1.0)
-side = torch.cuda.Stream()
+side = torch.cuda.Stream(priority=-1)
 red._post = side
-red._arena32 = arena32
-red._n_weights = n
 T, D, F = 1024, 2304, 9216
 x = torch.randn(T, D, device=dev).bfloat16()
 w1 = torch.randn(F, D, device=dev).bfloat16()
+wq = torch.randn(D, D, device=dev).bfloat16()
 dy = torch.randn(T, D, device=dev).bfloat16()
 h = torch.randn(T, F, device=dev).bfloat16()
 o1 = torch.empty(T, F, device=dev, dtype=torch.bfloat16)
+o2 = torch.empty(T, D, device=dev, dtype=torch.bfloat16)
 gw = torch.empty(D, F, device=dev, dtype=torch.float32)
 big = torch.randn(32 << 20, device=dev)
 big16 = torch.empty(32 << 20, device=dev, dtype=torch.bfloat16)
+SMS = torch.cuda.get_device_properties(dev).multi_processor_count
 
 
 def compute_gemm():
     ops.gemm(x, w1, out=o1)                                             # fwd 1024x9216x2304
     ops.gemm(dy, h, a_major=1, b_major=1, epilogue=ops.EPI_F32, out=gw)  # wgrad 2304x9216x1024
+    ops.gemm(x, wq, out=o2)                                             # 1024x2304x2304 (72 pair tiles)
 
 
 def compute_cast():
@@ -51,17 +53,12 @@ def comm_none(reps):
     pass
 
 
-def mk_nvls(blocks, threads, nbytes):
+def mk_nvls(blocks, threads, excl, nbytes):
     def f(reps):
-        red.nvls_blocks, red.nvls_threads = blocks, threads
+        red.nvls_blocks, red.nvls_threads, red.exclusive_sms = blocks, threads, excl
         for _ in range(reps):
-            red._launch_nvls(0, nbytes, True, 0)
+            red._launch_nvls(nv["off16"], nbytes, True, nv["mc"])
     return f
-
-
-def comm_convert(reps):
-    for _ in range(reps):
-        _lib.check(_lib.lib().b200b_bf16_to_f32(plain16.data_ptr(), arena32.data_ptr(), n, 1.0, side.cuda_stream), "cv")
 
 
 def comm_nccl(reps):
@@ -70,13 +67,18 @@ def comm_nccl(reps):
             dist.all_reduce(plain16, op=dist.ReduceOp.AVG)
 
 
-variants = [("none", comm_none, 0), ("nvls_32x512_128MB", mk_nvls(32, 512, 2 * n), 12),
-            ("nvls_148x128_128MB", mk_nvls(148, 128, 2 * n), 12), ("nvls_8x512_128MB", mk_nvls(8, 512, 2 * n), 6),
-            ("nvls_barrier_only_32x512", mk_nvls(32, 512, 16 * 1024), 400), ("convert_only", comm_convert, 60),
-            ("nccl_128MB", comm_nccl, 12)]
+# (name, comm fn, reps, compute SM limit)
+variants = [("none_148", comm_none, 0, 0), ("none_144", comm_none, 0, SMS - 4),
+            ("nvls_4x1024_excl_limit144", mk_nvls(4, 1024, True, 2 * n), 10, SMS - 4),
+            ("nvls_2x1024_excl_limit146", mk_nvls(2, 1024, True, 2 * n), 8, SMS - 2),
+            ("nvls_4x1024_excl_nolimit", mk_nvls(4, 1024, True, 2 * n), 10, 0),
+            ("nvls_4x1024_shared_limit144", mk_nvls(4, 1024, False, 2 * n), 10, SMS - 4),
+            ("nvls_148x128_shared", mk_nvls(148, 128, False, 2 * n), 10, 0),
+            ("nccl_128MB", comm_nccl, 12, 0)]
 out = []
-for cname, cfn, creps in (("gemm_pair", compute_gemm, 60), ("cast_128MB", compute_cast, 60)):
-    for vname, vfn, vreps in variants:
+for cname, cfn, creps in (("gemm_trio", compute_gemm, 60), ("cast_128MB", compute_cast, 60)):
+    for vname, vfn, vreps, limit in variants:
+        _lib.lib().b200b_set_sm_limit(limit)
         for _ in range(3):
             cfn()
         torch.cuda.synchronize(); dist.barrier()
@@ -91,8 +93,10 @@ for cname, cfn, creps in (("gemm_pair", compute_gemm, 60), ("cast_128MB", comput
         e1.record()
         torch.cuda.synchronize()
         out.append({"compute": cname, "comm": vname, "compute_us_per_iter": round(e0.elapsed_time(e1) / creps * 1e3, 1),
-                    "comm_total_ms": round(s0.elapsed_time(s1), 2), "compute_total_ms": round(e0.elapsed_time(e1), 2)})
+                    "comm_total_ms": round(s0.elapsed_time(s1), 2), "compute_total_ms": round(e0.elapsed_time(e1), 2),
+                    "comm_GBs": round(vreps * 2 * n / (s0.elapsed_time(s1) * 1e-3) / 1e9, 1) if vreps else None})
         dist.barrier()
+_lib.lib().b200b_set_sm_limit(0)
 if rank == 0:
     for o in out:
         print(json.dumps(o), flush=True)

@@ -53,10 +53,14 @@ def _worker(rank, world, port, out):
     broadcast_parameters(m)
     want = torch.stack([grads(*shard(r)) for r in range(world)]).mean(0)      # no exchange
     res = {}
-    for name, backend, dtype, tol in (("f32", "nccl", torch.float32, 1e-5), ("bf16", "nccl", torch.bfloat16, 1.5e-2),
-                                      ("nvls_f32", "nvls", torch.float32, 1e-5),
-                                      ("nvls_bf16", "nvls", torch.bfloat16, 1.5e-2)):
-        red = enable_data_parallel(m, bucket_bytes=8 << 20, grad_dtype=dtype, backend=backend)
+    for name, backend, dtype, tol, kw in (
+            ("f32", "nccl", torch.float32, 1e-5, {}), ("bf16", "nccl", torch.bfloat16, 1.5e-2, {}),
+            ("nvls_f32", "nvls", torch.float32, 1e-5, {}), ("nvls_bf16", "nvls", torch.bfloat16, 1.5e-2, {}),
+            # fp32 multicast straight into .grad, and the exchange on 4 SMs of its own (CTA pairs)
+            ("nvls_bf16_mc32", "nvls", torch.bfloat16, 1.5e-2, dict(fp32_multicast=True)),
+            ("nvls_bf16_excl", "nvls", torch.bfloat16, 1.5e-2,
+             dict(fp32_multicast=True, exclusive_sms=True, nvls_blocks=4, nvls_threads=1024))):
+        red = enable_data_parallel(m, bucket_bytes=8 << 20, grad_dtype=dtype, backend=backend, **kw)
         got = grads(*shard(rank))
         torch.cuda.synchronize()
         err = float((got - want).norm() / want.norm())

@@ -19,6 +19,8 @@ EPI_BF16_BIAS_GELU = 1
 EPI_F32_BIAS_RESID = 2
 EPI_BF16_DGELU = 3
 EPI_F32 = 4
+NVLS_OUT_MULTICAST = 1      # B200B_NVLS_OUT_MULTICAST
+NVLS_EXCLUSIVE_SMS = 2      # B200B_NVLS_EXCLUSIVE_SMS
 
 
 class GemmArgs(C.Structure):
@@ -129,7 +131,11 @@ def _declare(lib) -> None:
     lib.b200b_allreduce_nvls_flag_bytes.argtypes = []
     lib.b200b_allreduce_nvls.restype = C.c_int
     lib.b200b_allreduce_nvls.argtypes = [C.POINTER(NvlsComm), C.c_int, C.c_int64, C.c_int64, C.c_float, C.c_void_p,
-                                         C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+                                         C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p]
+    lib.b200b_set_sm_limit.restype = None
+    lib.b200b_set_sm_limit.argtypes = [C.c_int]
+    lib.b200b_get_sm_limit.restype = C.c_int
+    lib.b200b_get_sm_limit.argtypes = []
     lib.b200b_colsum_finalize.restype = C.c_int
     lib.b200b_colsum_finalize.argtypes = [C.POINTER(ColsumTask), C.c_int, C.c_void_p]
     lib.b200b_attention_fwd.restype = C.c_int

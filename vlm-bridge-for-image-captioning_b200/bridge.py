@@ -500,17 +500,27 @@ class BridgeLite(nn.Module):
             raise RuntimeError("bridge parameters were modified in place between forward and backward")
         B, L, D = fdims.batch, fdims.len_text, fdims.dim
         d = d_out.detach().to(torch.float32).contiguous().view(B * L, D)
-        garena = torch.empty(lay.total, device=dev, dtype=torch.float32)
-        gbase = garena.data_ptr()
         # data parallel: `reducer` exchanges gradient ranges as soon as their kernels are enqueued.
         # With a bf16 exchange the weight-gradient GEMMs write a bf16 arena (the values autocast gives
-        # these gradients in the reference) and the reducer converts the averaged buckets into garena.
+        # these gradients in the reference) and the averaged buckets end up as fp32 in garena. The nvls
+        # transport owns both arenas (symmetric memory, reused every step).
         reducer = self._bucket_hook
+        garena = None
         g16 = None   # arena the weight-gradient GEMMs write when it is not garena itself
         if reducer is not None and reducer.world_size > 1:
-            g16 = reducer.weight_arena(lay.n_weights, lay.total - lay.n_weights, dev)
-            if g16 is None and reducer.wgrad_bf16:
+            garena, g16 = reducer.arenas(lay.n_weights, lay.total, dev)
+            if garena is not None:
+                # a persistent arena: gradients still referenced from an earlier step (accumulation
+                # without zero_grad) must not be overwritten in place
+                lo_, hi_ = garena.data_ptr(), garena.data_ptr() + 4 * lay.total
+                for _, p_ in self._named_params():
+                    if p_.grad is not None and lo_ <= p_.grad.data_ptr() < hi_ and not torch.cuda.is_current_stream_capturing():
+                        p_.grad = p_.grad.clone()
+            elif reducer.wgrad_bf16:
                 g16 = torch.empty(lay.n_weights, device=dev, dtype=torch.bfloat16)
+        if garena is None:
+            garena = torch.empty(lay.total, device=dev, dtype=torch.float32)
+        gbase = garena.data_ptr()
         wgrad_bf16 = g16 is not None and g16.dtype == torch.bfloat16
         g16base = g16.data_ptr() if g16 is not None else 0
         g16size = g16.element_size() if g16 is not None else 4

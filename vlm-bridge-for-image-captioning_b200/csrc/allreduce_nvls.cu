@@ -15,6 +15,16 @@
 //               .grad arena, block b converting exactly the units whose producers it has just
 //               synchronised with in barrier B
 // Per rank and direction the links carry ~(1 + 1/world)x the bucket (a ring carries 2*(world-1)/world).
+//
+// B200B_NVLS_OUT_MULTICAST: the broadcast goes out as fp32 to a second symmetric buffer (the .grad
+// arena) instead of in place as bf16: 8-byte multimem.ld_reduce of 4 bf16 -> 16-byte multimem.st of
+// 4 fp32, both fully coalesced. The incoming link carries 2x the broadcast bytes, but the separate
+// bf16 -> fp32 pass over the whole arena (0.95 GB of HBM traffic per step, the single worst neighbour
+// of the backward GEMMs: profiles/r01_exp_overlap_2gpu_v1.jsonl) disappears.
+// B200B_NVLS_EXCLUSIVE_SMS: the grid is launched as CTA pairs (clusters of 2 = one TPC) that claim
+// their SMs' whole shared memory, so no compute CTA is ever co-resident; together with
+// b200b_set_sm_limit() on the compute side (the persistent GEMMs then leave those TPCs alone) the
+// exchange neither slows the statically scheduled GEMM CTAs nor waits for them.
 // The kernel uses no shared memory and ~32 registers per thread, so its CTAs share SMs with the
 // 1-CTA-per-SM GEMMs of the backward pass instead of evicting them; the caller picks the shape of the
 // grid -- many small CTAs spread the outstanding multimem requests thinly over all SMs, which matters
@@ -24,6 +34,7 @@
 // written only by block b of rank q. Values are the monotonically increasing collective number
 // (same sequence on every rank), so flags are never reset.
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/b200_bridge.h"
 #include "common.cuh"
@@ -31,13 +42,14 @@
 
 namespace b200b {
 
-constexpr int kNvlsMaxThreads = 512;
+constexpr int kNvlsMaxThreads = 1024;
 constexpr int kNvlsUnroll = 4;  // 16-byte units in flight per thread
 
 struct NvlsParams {
   uint64_t mc;                           // multicast address of the first unit of the bucket
   const uint4* local;                    // this rank's own copy of the bucket (same units)
   float4* out_f32;                       // fp32 destination of the whole bucket, or nullptr
+  uint64_t mc_out;                       // B200B_NVLS_OUT_MULTICAST: multicast address of the fp32 destination
   uint32_t* flags[B200B_NVLS_MAX_RANKS]; // every rank's flag array as mapped in this process
   long long units;                       // 16-byte units in the bucket
   long long per;                         // units per shard
@@ -166,13 +178,53 @@ __global__ void __launch_bounds__(kNvlsMaxThreads) allreduce_nvls_kernel(const N
   }
 }
 
+
+__device__ __forceinline__ uint2 multimem_ld_reduce_bf16x4(uint64_t addr) {
+  uint2 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v2.bf16x2 {%0,%1}, [%2];"
+               : "=r"(v.x), "=r"(v.y)
+               : "l"(addr)
+               : "memory");
+  return v;
+}
+
+// bf16 bucket in, fp32 broadcast out (B200B_NVLS_OUT_MULTICAST). Units are 8 bytes (4 bf16 -> 4 fp32).
+constexpr int kBcastUnroll = 16;
+__global__ void __launch_bounds__(kNvlsMaxThreads) allreduce_nvls_bcast32_kernel(const NvlsParams p) {
+  const uint32_t epoch = p.epoch + (p.epoch_base != nullptr ? __ldcg(p.epoch_base) : 0u);
+  barrier_blocks(p, epoch, 0);
+  const int nthreads = (int)blockDim.x;
+  const long long stride = (long long)gridDim.x * nthreads;
+  const long long units = 2 * p.units;  // 8-byte units
+  const long long per = (units + p.world - 1) / p.world;
+  const long long lo = (long long)p.rank * per;
+  const long long hi = min(lo + per, units);
+  for (long long i = lo + (long long)blockIdx.x * nthreads + threadIdx.x; i < hi; i += kBcastUnroll * stride) {
+    uint2 v[kBcastUnroll];
+#pragma unroll
+    for (int u = 0; u < kBcastUnroll; ++u)
+      if (i + u * stride < hi) v[u] = multimem_ld_reduce_bf16x4(p.mc + 8ull * (unsigned long long)(i + u * stride));
+#pragma unroll
+    for (int u = 0; u < kBcastUnroll; ++u)
+      if (i + u * stride < hi) {
+        uint4 f;
+        f.x = __float_as_uint(bf16_lo(v[u].x) * p.scale);
+        f.y = __float_as_uint(bf16_hi(v[u].x) * p.scale);
+        f.z = __float_as_uint(bf16_lo(v[u].y) * p.scale);
+        f.w = __float_as_uint(bf16_hi(v[u].y) * p.scale);
+        multimem_st(p.mc_out + 16ull * (unsigned long long)(i + u * stride), f);
+      }
+  }
+  barrier_blocks(p, epoch, 1);
+}
+
 }  // namespace b200b
 
 using namespace b200b;
 
 extern "C" int b200b_allreduce_nvls(const b200b_nvls_comm* comm, int dtype, int64_t byte_offset, int64_t bytes,
                                     float scale, float* out_f32, uint32_t epoch, const uint32_t* epoch_base,
-                                    int blocks, int threads, void* stream_) {
+                                    int blocks, int threads, uint32_t flags, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (comm == nullptr || comm->multicast_base == nullptr || comm->local_base == nullptr) {
     set_last_error("allreduce_nvls: null communicator / buffer");
@@ -202,6 +254,16 @@ extern "C" int b200b_allreduce_nvls(const b200b_nvls_comm* comm, int dtype, int6
     set_last_error("allreduce_nvls: out_f32 needs a bf16 bucket and a 16-byte aligned destination");
     return B200B_ERR_ARG;
   }
+  const bool out_mc = (flags & B200B_NVLS_OUT_MULTICAST) != 0;
+  const bool exclusive = (flags & B200B_NVLS_EXCLUSIVE_SMS) != 0;
+  if (out_mc && out_f32 == nullptr) {
+    set_last_error("allreduce_nvls: B200B_NVLS_OUT_MULTICAST needs the multicast address of the fp32 destination");
+    return B200B_ERR_ARG;
+  }
+  if (exclusive && (blocks % 2) != 0) {
+    set_last_error("allreduce_nvls: B200B_NVLS_EXCLUSIVE_SMS launches CTA pairs: blocks must be even");
+    return B200B_ERR_ARG;
+  }
   if (blocks <= 0 || blocks > B200B_NVLS_MAX_BLOCKS || threads < 32 || threads > kNvlsMaxThreads || (threads % 32)) {
     set_last_error("allreduce_nvls: blocks must be in 1..%d and threads a multiple of 32 in 32..%d", B200B_NVLS_MAX_BLOCKS,
                    kNvlsMaxThreads);
@@ -223,11 +285,43 @@ extern "C" int b200b_allreduce_nvls(const b200b_nvls_comm* comm, int dtype, int6
   p.epoch_base = epoch_base;
   p.rank = comm->rank;
   p.world = comm->world;
-  if (dtype == B200B_DTYPE_BF16)
-    allreduce_nvls_kernel<true><<<blocks, threads, 0, stream>>>(p);
-  else
-    allreduce_nvls_kernel<false><<<blocks, threads, 0, stream>>>(p);
-  return check_launch("allreduce_nvls", stream);
+  p.mc_out = out_mc ? reinterpret_cast<uint64_t>(out_f32) : 0;
+  if (out_mc) p.out_f32 = nullptr;
+  void (*kern)(const NvlsParams) = out_mc ? allreduce_nvls_bcast32_kernel
+                                   : (dtype == B200B_DTYPE_BF16 ? allreduce_nvls_kernel<true> : allreduce_nvls_kernel<false>);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (exclusive) {
+    // claim the SM: no CTA that needs more than the few KB left can become co-resident
+    constexpr int kHogBytes = 200 * 1024;
+    static bool attr_done[3] = {false, false, false};
+    const int ki = out_mc ? 0 : (dtype == B200B_DTYPE_BF16 ? 1 : 2);
+    if (!attr_done[ki]) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kHogBytes);
+      if (e != cudaSuccess) {
+        set_last_error("allreduce_nvls: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        return (int)e;
+      }
+      attr_done[ki] = true;
+    }
+    cfg.dynamicSmemBytes = kHogBytes;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  if (e != cudaSuccess) {
+    set_last_error("allreduce_nvls: launch failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return check_launch(out_mc ? "allreduce_nvls_bcast32" : "allreduce_nvls", stream);
 }
 
 extern "C" size_t b200b_allreduce_nvls_flag_bytes(void) {

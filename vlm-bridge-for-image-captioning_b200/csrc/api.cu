@@ -14,6 +14,7 @@ namespace b200b {
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_sm_limit{0};  // b200b_set_sm_limit: 0 = all SMs
 
 void set_last_error(const char* fmt, ...) {
   va_list ap;
@@ -72,13 +73,16 @@ int device_sm_count(int* out) {
     cached_sms = sms;
     cached_dev = dev;
   }
-  *out = cached_sms;
+  const int limit = g_sm_limit.load(std::memory_order_relaxed);
+  *out = (limit > 0 && limit < cached_sms) ? limit : cached_sms;
   return B200B_OK;
 }
 
 }  // namespace b200b
 
 extern "C" int b200b_abi_version(void) { return B200B_ABI_VERSION; }
+extern "C" void b200b_set_sm_limit(int sms) { b200b::g_sm_limit.store(sms > 0 ? sms : 0, std::memory_order_relaxed); }
+extern "C" int b200b_get_sm_limit(void) { return b200b::g_sm_limit.load(std::memory_order_relaxed); }
 extern "C" const char* b200b_last_error(void) { return b200b::g_err; }
 extern "C" uint64_t b200b_launch_count(void) { return b200b::g_launches.load(std::memory_order_relaxed); }
 

@@ -20,11 +20,13 @@ gradient arena that `BridgeLite` writes during backward:
 
 Two transports:
 * `backend="nvls"` (default when the process group's GPUs offer NVSwitch multicast): the library's
-  own all-reduce kernel (csrc/allreduce_nvls.cu) on a symmetric gradient buffer -- in-switch
-  reduction (multimem.ld_reduce / multimem.st), ~1x the bucket per link direction instead of a
-  ring's 2(N-1)/N, fused with the bf16 -> fp32 conversion, and small enough (no shared memory) to
-  share SMs with the backward GEMMs. torch.distributed's symmetric memory is used only to allocate
-  and map the buffers.
+  own all-reduce kernel (csrc/allreduce_nvls.cu) on symmetric gradient buffers -- in-switch
+  reduction (multimem.ld_reduce) and multicast store (multimem.st) of the bf16 buckets, ~1x the
+  bucket per link direction instead of a ring's 2(N-1)/N, followed by a bf16 -> fp32 pass into the
+  `.grad` arena. Its CTAs use no shared memory and few registers, so they share SMs with the backward
+  kernels. Measured alternatives kept as options: an fp32 multicast straight into `.grad`
+  (`fp32_multicast`) and SMs reserved for the exchange (`exclusive_sms`); see `enable_data_parallel`.
+  torch.distributed's symmetric memory is used only to allocate and map the buffers.
 * `backend="nccl"`: torch.distributed.all_reduce per bucket (also what the CPU/gloo tests drive).
 """
 from __future__ import annotations
@@ -42,8 +44,8 @@ class GradBucketReducer:
     """Driven by `BridgeLite._run_backward`: begin() -> weights_ready()* / flush() / vectors_ready()* -> finish()."""
 
     def __init__(self, process_group: Optional[dist.ProcessGroup] = None, bucket_bytes: int = 32 << 20,
-                 grad_dtype: torch.dtype = torch.bfloat16, backend: str = "auto", nvls_blocks: int = 148,
-                 nvls_threads: int = 128):
+                 grad_dtype: torch.dtype = torch.bfloat16, backend: str = "auto", nvls_blocks: int = 32,
+                 nvls_threads: int = 512, exclusive_sms: bool = False, fp32_multicast: bool = False):
         if grad_dtype not in (torch.bfloat16, torch.float32):
             raise ValueError("grad_dtype must be torch.bfloat16 or torch.float32")
         if backend not in ("auto", "nvls", "nccl"):
@@ -61,8 +63,9 @@ class GradBucketReducer:
         self.backend = backend
         self.nvls_blocks = int(nvls_blocks)
         self.nvls_threads = int(nvls_threads)
+        self.exclusive_sms = bool(exclusive_sms) and self.nvls_blocks % 2 == 0
+        self.fp32_multicast = bool(fp32_multicast)   # False: bf16 result in place + a separate bf16 -> fp32 pass
         self._nvls = None               # (comm struct, symmetric byte buffer, flag buffer, handles)
-        self.fuse_convert = False       # convert inside the exchange kernel (few CTAs) or as its own launch
         self.trace: Optional[list] = None   # set to [] to record per-bucket CUDA events (diagnostics)
         self._t0 = None
         self._epoch = 0
@@ -87,31 +90,37 @@ class GradBucketReducer:
 
     def describe(self) -> str:
         kind = "bf16 buckets + fp32 vectors" if self.wgrad_bf16 else "fp32 buckets"
-        how = (f"own NVLS multimem kernel ({self.nvls_blocks} CTAs x {self.nvls_threads} threads)" if self.backend == "nvls"
-               else ("NCCL" if self._nccl else dist.get_backend(self.group)))
+        how = (f"own NVLS multimem kernel ({self.nvls_blocks} CTAs x {self.nvls_threads} threads"
+               f"{' on SMs of their own' if self.exclusive_sms else ''}"
+               f"{', fp32 multicast into .grad' if self.fp32_multicast else ', bf16 in place + fp32 pass'})"
+               if self.backend == "nvls" else ("NCCL" if self._nccl else dist.get_backend(self.group)))
         return (f"{how} all-reduce(avg), {kind}, >= {self.bucket_bytes >> 20} MiB per bucket, "
                 f"{self.buckets_per_step} collectives per step")
 
     # -- nvls transport: symmetric buffers ---------------------------------------------------------
-    def weight_arena(self, n_weights: int, n_vectors: int, device: torch.device) -> Optional[torch.Tensor]:
-        """The arena the weight-gradient GEMMs must write for this transport, or None if any
-        ordinary tensor will do (nccl). Allocated and mapped on every rank once."""
+    def arenas(self, n_weights: int, total: int, device: torch.device):
+        """(fp32 gradient arena [total], weight-gradient arena [n_weights] or None) the backward must
+        write for this transport, or (None, None) if ordinary tensors will do (nccl). Both live in one
+        symmetric allocation mapped on every rank: the fp32 arena is where `.grad` ends up (the exchange
+        multicasts the averaged values into it), the bf16 arena is what the weight-gradient GEMMs write.
+        Allocated once; reused by every step."""
         if self.backend != "nvls":
-            return None
+            return None, None
         esize = 2 if self.wgrad_bf16 else 4
-        if self._nvls is None or self._nvls["n_weights"] != n_weights or self._nvls["esize"] != esize:
-            self._nvls = self._nvls_setup(n_weights, n_vectors, esize, device)
-        return self._nvls["weights"]
+        nv = self._nvls
+        if nv is None or nv["n_weights"] != n_weights or nv["total"] != total or nv["esize"] != esize:
+            nv = self._nvls = self._nvls_setup(n_weights, total, esize, device)
+        return nv["arena32"], nv["weights16"]
 
-    def _nvls_setup(self, n_weights: int, n_vectors: int, esize: int, device: torch.device) -> dict:
+    def _nvls_setup(self, n_weights: int, total: int, esize: int, device: torch.device) -> dict:
         import torch.distributed._symmetric_memory as symm
 
         from . import _lib
 
         group = self.group if self.group is not None else dist.group.WORLD
-        wbytes = (n_weights * esize + 255) // 256 * 256
-        vbytes = (n_vectors * 4 + 255) // 256 * 256
-        buf = symm.empty(wbytes + vbytes, dtype=torch.uint8, device=device)
+        bytes32 = (total * 4 + 255) // 256 * 256
+        bytes16 = (n_weights * 2 + 255) // 256 * 256 if esize == 2 else 0
+        buf = symm.empty(bytes32 + bytes16, dtype=torch.uint8, device=device)
         hbuf = symm.rendezvous(buf, group.group_name)
         nflag = _lib.lib().b200b_allreduce_nvls_flag_bytes() // 4
         flags = symm.empty(nflag, dtype=torch.int32, device=device)
@@ -127,21 +136,23 @@ class GradBucketReducer:
         for q in range(self.world_size):
             comm.flags[q] = hflags.buffer_ptrs[q]
         comm.rank, comm.world = dist.get_rank(self.group), self.world_size
-        return dict(comm=comm, buf=buf, flags=flags, handles=(hbuf, hflags), n_weights=n_weights, esize=esize,
+        return dict(comm=comm, buf=buf, flags=flags, handles=(hbuf, hflags), n_weights=n_weights, total=total,
+                    esize=esize, mc=int(hbuf.multicast_ptr), off16=bytes32,
                     epoch_dev=torch.zeros(1, dtype=torch.int32, device=device),
-                    weights=buf[:n_weights * esize].view(torch.bfloat16 if esize == 2 else torch.float32),
-                    vectors=buf[wbytes:wbytes + n_vectors * 4].view(torch.float32), voff=wbytes)
+                    arena32=buf[:total * 4].view(torch.float32),
+                    weights16=buf[bytes32:bytes32 + n_weights * 2].view(torch.bfloat16) if esize == 2 else None)
 
-    def _launch_nvls(self, byte_offset: int, nbytes: int, bf16: bool, out_f32_ptr: int) -> None:
+    def _launch_nvls(self, byte_offset: int, nbytes: int, bf16: bool, out_multicast: int = 0) -> None:
         from . import _lib
 
         # collective number = (index within this step) + device counter advanced once per step by
         # finish(): identical for eager launches and for replays of a captured CUDA graph
         self._epoch += 1
+        flags = (_lib.NVLS_OUT_MULTICAST if out_multicast else 0) | (_lib.NVLS_EXCLUSIVE_SMS if self.exclusive_sms else 0)
         _lib.check(_lib.lib().b200b_allreduce_nvls(
             C.byref(self._nvls["comm"]), 0 if bf16 else 1, byte_offset, nbytes, 1.0 / self.world_size,
-            C.c_void_p(out_f32_ptr) if out_f32_ptr else None, self._epoch, self._nvls["epoch_dev"].data_ptr(),
-            self.nvls_blocks, self.nvls_threads, self._post.cuda_stream),
+            C.c_void_p(out_multicast) if out_multicast else None, self._epoch, self._nvls["epoch_dev"].data_ptr(),
+            self.nvls_blocks, self.nvls_threads, flags, self._post.cuda_stream),
             "allreduce_nvls")
 
     # -- protocol ------------------------------------------------------------------------------------
@@ -152,7 +163,8 @@ class GradBucketReducer:
         self.bytes_per_step = 0
         self.buckets_per_step = 0
         if arena32.is_cuda and self._post is None:
-            self._post = torch.cuda.Stream(device=arena32.device)
+            # highest priority: a bucket's exchange CTAs are placed before the next compute kernel's
+            self._post = torch.cuda.Stream(device=arena32.device, priority=-1)
         if self.trace is not None:
             self.trace.clear()
             self._t0 = torch.cuda.Event(enable_timing=True)
@@ -211,8 +223,6 @@ class GradBucketReducer:
             self.bytes_reduced += nbytes
             self.bytes_per_step += nbytes
             self.buckets_per_step += 1
-            from . import _lib
-
             nv = self._nvls
             self._post.wait_stream(torch.cuda.current_stream())
             if self.trace is not None:
@@ -221,22 +231,21 @@ class GradBucketReducer:
                 ev[1].record(self._post)
                 self.trace.append((lo, hi, nbytes, ev))
             with torch.cuda.stream(self._post):
-                if lo >= self._n_weights:             # fp32 vectors: stage through the symmetric buffer
-                    n = hi - lo
-                    nv["vectors"][:n].copy_(chunk)
-                    self._launch_nvls(nv["voff"], (n * 4 + 15) // 16 * 16, False, 0)
-                    chunk.copy_(nv["vectors"][:n])
-                elif chunk.dtype == torch.bfloat16:   # bf16 bucket, averaged, then written as fp32 .grad
-                    if self.fuse_convert:
-                        self._launch_nvls(2 * lo, nbytes, True, self._arena32.data_ptr() + 4 * lo)
-                    else:
-                        # the exchange needs few CTAs (link bound), the conversion many (HBM bound)
-                        self._launch_nvls(2 * lo, nbytes, True, 0)
-                        _lib.check(_lib.lib().b200b_bf16_to_f32(chunk.data_ptr(), self._arena32[lo:hi].data_ptr(), hi - lo,
-                                                                1.0, self._post.cuda_stream), "bf16_to_f32")
-                else:                                 # fp32 bucket of the symmetric arena, in place, then copied out
-                    self._launch_nvls(4 * lo, nbytes, False, 0)
-                    self._arena32[lo:hi].copy_(chunk)
+                if lo >= self._n_weights or chunk.dtype == torch.float32:
+                    # fp32 ranges of the symmetric .grad arena (bias / LayerNorm gradients, or everything
+                    # with grad_dtype=float32): averaged in place
+                    self._launch_nvls(4 * lo, (nbytes + 15) // 16 * 16, False)
+                elif self.fp32_multicast:
+                    # bf16 bucket: reduced in the switch, broadcast as fp32 into every rank's .grad arena
+                    self._launch_nvls(nv["off16"] + 2 * lo, nbytes, True, nv["mc"] + 4 * lo)
+                else:
+                    # bf16 bucket averaged in place (half the broadcast bytes on the links), then one
+                    # HBM-bound pass turns it into the fp32 .grad
+                    from . import _lib
+
+                    self._launch_nvls(nv["off16"] + 2 * lo, nbytes, True)
+                    _lib.check(_lib.lib().b200b_bf16_to_f32(chunk.data_ptr(), self._arena32[lo:hi].data_ptr(), hi - lo,
+                                                            1.0, self._post.cuda_stream), "bf16_to_f32")
             if self.trace is not None:
                 self.trace[-1][3][2].record(self._post)
             return
@@ -289,14 +298,34 @@ def _nvls_available() -> bool:
 
 def enable_data_parallel(module, process_group=None, bucket_bytes: int = 32 << 20,
                          grad_dtype: torch.dtype = torch.bfloat16, backend: str = "auto",
-                         nvls_blocks: int = 148, nvls_threads: int = 128) -> GradBucketReducer:
-    """Attach a bucketed all-reduce to `module` (a B200 BridgeLite). Returns the reducer."""
+                         nvls_blocks: int = 32, nvls_threads: int = 512, exclusive_sms: bool = False,
+                         fp32_multicast: bool = False) -> GradBucketReducer:
+    """Attach a bucketed all-reduce to `module` (a B200 BridgeLite). Returns the reducer.
+
+    Defaults are the fastest configuration measured on B200 (profiles/r01_dp_transport_sweep.md): the
+    own NVLS kernel with 32 CTAs x 512 threads sharing SMs with the backward, bf16 result in place and
+    a bf16 -> fp32 pass per bucket. `fp32_multicast=True` broadcasts fp32 straight into `.grad` (no
+    conversion pass, twice the broadcast bytes on the links); `exclusive_sms=True` sets `nvls_blocks`
+    SMs aside for the exchange (CTA pairs claiming whole SMs, the persistent GEMMs limited to the
+    rest via b200b_set_sm_limit until `disable_data_parallel`) -- interference drops to ~+10 % but a
+    handful of SMs cannot issue multimem requests fast enough (~13 GB/s per SM)."""
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised")
-    reducer = GradBucketReducer(process_group, bucket_bytes, grad_dtype, backend, nvls_blocks, nvls_threads)
+    reducer = GradBucketReducer(process_group, bucket_bytes, grad_dtype, backend, nvls_blocks, nvls_threads,
+                                exclusive_sms, fp32_multicast)
     module._bucket_hook = reducer
+    if reducer.backend == "nvls" and reducer.exclusive_sms and reducer.world_size > 1 and torch.cuda.is_available():
+        from . import _lib
+
+        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        _lib.lib().b200b_set_sm_limit(sms - reducer.nvls_blocks)
     return reducer
 
 
 def disable_data_parallel(module) -> None:
+    reducer = getattr(module, "_bucket_hook", None)
     module._bucket_hook = None
+    if reducer is not None and reducer.backend == "nvls" and reducer.exclusive_sms and torch.cuda.is_available():
+        from . import _lib
+
+        _lib.lib().b200b_set_sm_limit(0)
