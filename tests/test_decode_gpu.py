@@ -1,0 +1,97 @@
+"""Caption decode over the cached vision K/V: the per-image cache, the packed
+decode layout, the K/V-streaming cross-attention kernel and the batched greedy driver.
+
+The frozen language model is outside the hot path; as in oracle.greedy_decode_bridge_only it is
+replaced by a fixed embedding table and a fixed linear read-out, so the loop
+(embed prefix -> bridge -> logits of the last position -> argmax -> append) is the reference's
+(full_model.py:241-363) with the bridge as the only arithmetic under test.
+
+Tolerances: cached vs uncached bridge output: bit-exact (same kernels' arithmetic in the same order);
+CUDA (bf16 operands, fp32 accumulate) vs fp32 oracle: max|d|/max|ref| <= 2e-2; greedy token ids equal
+to the oracle's wherever the oracle's top-2 logit margin exceeds the bf16 logit error bound
+(2e-2 * max|logit|), which must hold for at least 90 % of the steps.
+"""
+import pytest
+import torch
+
+from oracle import bridge_oracle as O
+
+pytestmark = pytest.mark.gpu
+CFG = dict(vision_dim=1024, language_dim=2304, num_blocks=2, num_heads_cross=8, num_heads_self=18)
+
+
+def _model(sd):
+    from vlm_bridge_b200 import BridgeLite
+
+    m = BridgeLite(dropout=0.0, **CFG)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("s", [1, 5, 16, 17, 33, 64, 70])
+def test_cached_forward_is_bit_exact_and_matches_oracle(s):
+    from vlm_bridge_b200 import VisionKVCache
+
+    sd = O.init_state_dict(0)
+    g = torch.Generator().manual_seed(100 + s)
+    B, Nv = 3, 257
+    vision = torch.randn(B, Nv, 1024, generator=g)
+    text = torch.randn(B, s, 2304, generator=g)
+    m = _model(sd)
+    with torch.no_grad():
+        cache = VisionKVCache(m, vision.cuda())
+        y_cached = m(vision.cuda(), text.cuda(), kv_cache=cache)
+        y_plain = m(vision.cuda(), text.cuda())
+    assert cache.is_current()
+    assert torch.equal(y_cached, y_plain)
+    if s in (1, 17, 64):
+        y_ref = O.bridge_forward_cached(sd, O.vision_kv(sd, vision), text)
+        assert float((y_cached.cpu() - y_ref).abs().max() / y_ref.abs().max()) <= 2e-2
+
+
+def test_greedy_decode_matches_oracle_and_is_sync_free_batched():
+    from vlm_bridge_b200 import greedy_decode
+
+    sd = O.init_state_dict(1)
+    g = torch.Generator().manual_seed(7)
+    B, Nv, V, steps = 4, 257, 512, 10
+    vision = torch.randn(B, Nv, 1024, generator=g)
+    embed = torch.randn(V, 2304, generator=g)
+    head = torch.randn(V, 2304, generator=g) / 48.0
+    m = _model(sd)
+    embed_d, head_d = embed.cuda(), head.cuda()
+    ids, lengths = greedy_decode(m, vision.cuda(), lambda t: embed_d[t], lambda h: h[:, -1, :] @ head_d.t(),
+                                 bos_token_id=2, eos_token_id=1, max_new_tokens=steps)
+    ids_nc, _ = greedy_decode(m, vision.cuda(), lambda t: embed_d[t], lambda h: h[:, -1, :] @ head_d.t(),
+                              bos_token_id=2, eos_token_id=1, max_new_tokens=steps, use_cache=False)
+    assert torch.equal(ids, ids_nc)                      # cache on / off: identical token ids
+    assert ids.shape == (B, steps + 1) and bool((ids[:, 0] == 2).all())
+    # teacher-forced comparison with the fp32 oracle on the CUDA path's own prefixes
+    ids_c = ids.cpu()
+    decided = agree = 0
+    for step in range(steps):
+        y = O.bridge_forward(sd, vision, embed[ids_c[:, :step + 1]])
+        logits = y[:, -1, :] @ head.t()
+        top2 = logits.topk(2, dim=-1).values
+        margin = top2[:, 0] - top2[:, 1]
+        clear = margin > 2e-2 * logits.abs().max(dim=-1).values
+        decided += int(clear.sum())
+        agree += int((logits.argmax(-1)[clear] == ids_c[:, step + 1][clear]).sum())
+    assert decided >= 0.9 * B * steps, (decided, B * steps)
+    assert agree == decided, (agree, decided)
+    # lengths: first EOS (token 1) per row, else the full length
+    for b in range(B):
+        row = ids_c[b, 1:].tolist()
+        want = (row.index(1) + 1) if 1 in row else steps + 1
+        assert int(lengths[b]) == want
+
+
+def test_stale_cache_is_detected():
+    from vlm_bridge_b200 import VisionKVCache
+
+    m = _model(O.init_state_dict(2))
+    cache = VisionKVCache(m, torch.randn(1, 17, 1024).cuda())
+    assert cache.is_current()
+    with torch.no_grad():
+        next(m.parameters()).add_(1e-3)
+    assert not cache.is_current()
