@@ -438,6 +438,12 @@ def run_b200_arm(args) -> int:
             except Exception as e:  # noqa: BLE001
                 line["decode"] = {"error": repr(e)[:300]}
         model.train()
+        # ---- whole training step with the fused optimizer, N=1 only ---------
+        if world == 1 and not args.no_train_step:
+            try:
+                line["train_step"] = bench_train_step(model, step, vision_d, text_d, args.steps)
+            except Exception as e:  # noqa: BLE001
+                line["train_step"] = {"error": repr(e)[:300]}
         # ---- CPU baseline beside it (N=1 only) ---------------------------------------------------
         if world == 1 and not args.no_cpu_baseline:
             v, ms, cores, sample = cpu_bridge_samples_per_s(steps=3, warmup=1, budget_s=25.0)
@@ -448,6 +454,47 @@ def run_b200_arm(args) -> int:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def bench_train_step(model, step, vision_d, text_d, steps: int) -> dict:
+    """fwd + bwd + BridgeAdamW.step (global-norm clip 0.3 + AdamW, config/training-default.yaml values), eager
+    launches. The optimizer writes the bf16 operand copy of the weights, so the forward's re-cast pass is
+    skipped -- unlike the headline step above, which re-casts every step to stand in for an optimizer."""
+    import torch
+
+    from vlm_bridge_b200 import BridgeAdamW
+
+    opt = BridgeAdamW(model, lr=1e-5, weight_decay=0.01, max_grad_norm=0.3)
+    params = list(model.parameters())
+
+    def train_step():
+        for p in params:
+            p.grad = None
+        loss = model(vision_d, text_d).float().square().mean()
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        train_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        train_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    e0.record()
+    for _ in range(steps):
+        opt.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_opt = e0.elapsed_time(e1) / steps
+    return {"metric": "bridge training step samples/sec (fwd + bwd + fused clip/AdamW)", "value": B_PER_GPU / (ms * 1e-3),
+            "unit": "samples/s", "ms_per_step": ms, "optimizer_ms": ms_opt,
+            "optimizer_hbm_GBs": (158160384 * 32 + model._layout.n_weights * 2) / (ms_opt * 1e-3) / 1e9,
+            "launch_mode": "eager", "grad_norm_last": float(opt.last_grad_norm)}
 
 
 def bench_decode(model, dev, peaks, _lib) -> dict:
@@ -518,6 +565,7 @@ def main() -> int:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--dp-backend", default="auto", choices=["auto", "nvls", "nccl"],
                     help="transport of the gradient exchange: own NVLS multimem kernel, or NCCL")

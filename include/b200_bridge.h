@@ -319,6 +319,31 @@ int b200b_bridge_kv_backward(const b200b_bridge_dims* dims, const void* vision_b
                              const void* dkv, void* dwkv_all, float* dbkv_all, void* workspace,
                              size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------- *
+ * Optimizer step over the flat arenas. Replaces GradScaler.unscale_, the
+ * gradient-norm loop, clip_grad_norm_ and torch.optim.AdamW.step of the reference training step
+ * (core_training_loop.py:84-104, training_setup.py:248-254) with two launches.
+ *
+ * b200b_grad_sqnorm: out2[0] = sum of grad[i]^2 (deterministic order), out2[1] = 1.0 if that is not
+ * finite else 0.0. `workspace` (b200b_grad_sqnorm_workspace_bytes(), zero-filled once by the caller)
+ * holds the partial sums and a ticket counter the kernel resets itself.
+ *
+ * b200b_adamw_fused: one pass over n elements of param / grad / exp_avg / exp_avg_sq with
+ * torch.optim.AdamW's arithmetic (decoupled weight decay, bias corrections from `step` >= 1); the
+ * first n_bf16 elements of the updated param are also written as bf16 to weights_bf16 (the GEMM
+ * operand copy). Gradients are used as grad / *grad_scale (grad_scale NULL = 1); with sqnorm2 (the
+ * output of b200b_grad_sqnorm on the same gradients) they are clipped to max_grad_norm as
+ * torch.nn.utils.clip_grad_norm_ does (max_grad_norm <= 0: no clipping) and the whole step is skipped
+ * when the norm is not finite; it is also skipped when *found_inf != 0 (GradScaler). All scalars that
+ * change every step and would otherwise need a host sync are read from device memory. */
+size_t b200b_grad_sqnorm_workspace_bytes(void);
+int b200b_grad_sqnorm(const float* grad, int64_t n, void* workspace, size_t workspace_bytes, float* out2,
+                      void* stream);
+int b200b_adamw_fused(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* weights_bf16,
+                      int64_t n, int64_t n_bf16, const float* sqnorm2, float max_grad_norm,
+                      const float* grad_scale, const float* found_inf, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, int64_t step, void* stream);
+
 /* out f32 [n] = scale * in bf16 [n] (n % 8 == 0): turns an exchanged bf16 gradient bucket into
  * the fp32 .grad the optimizer reads. */
 int b200b_bf16_to_f32(const void* in_bf16, float* out, int64_t n, float scale, void* stream);

@@ -9,3 +9,4 @@ from .bridge import (BridgeBlock, BridgeLite, MultiHeadCrossAttention,  # noqa: 
 from .decode import greedy_decode  # noqa: E402,F401
 from .graph import GraphedBridgeStep  # noqa: E402,F401
 from .kv_cache import VisionKVCache  # noqa: E402,F401
+from .optim import BridgeAdamW  # noqa: E402,F401

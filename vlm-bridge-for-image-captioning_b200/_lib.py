@@ -132,6 +132,13 @@ def _declare(lib) -> None:
     lib.b200b_allreduce_nvls.restype = C.c_int
     lib.b200b_allreduce_nvls.argtypes = [C.POINTER(NvlsComm), C.c_int, C.c_int64, C.c_int64, C.c_float, C.c_void_p,
                                          C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p]
+    lib.b200b_grad_sqnorm_workspace_bytes.restype = C.c_size_t
+    lib.b200b_grad_sqnorm_workspace_bytes.argtypes = []
+    lib.b200b_grad_sqnorm.restype = C.c_int
+    lib.b200b_grad_sqnorm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.b200b_adamw_fused.restype = C.c_int
+    lib.b200b_adamw_fused.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_int64, C.c_void_p, C.c_float, C.c_void_p,
+                                                          C.c_void_p] + [C.c_float] * 5 + [C.c_int64, C.c_void_p]
     lib.b200b_set_sm_limit.restype = None
     lib.b200b_set_sm_limit.argtypes = [C.c_int]
     lib.b200b_get_sm_limit.restype = C.c_int
