@@ -165,3 +165,55 @@ def test_native_library_is_what_runs():
     with pytest.raises(RuntimeError):
         BridgeLite(vision_dim=32, language_dim=64, num_heads_cross=1, num_heads_self=1)(torch.randn(1, 4, 32),
                                                                                      torch.randn(1, 3, 64))
+
+
+def test_c5_vision_length_and_single_token():
+    """high-resolution vision length (BASELINE config 5: 1370 patch tokens) and a one-token prefix
+    (rows < one MMA tile everywhere) through forward + backward"""
+    cfg = dict(vision_dim=1024, language_dim=2304, num_blocks=2, num_heads_cross=8, num_heads_self=18)
+    sd = O.init_state_dict(5)
+    g = torch.Generator().manual_seed(55)
+    _check_fwd_bwd(cfg, sd, torch.randn(1, 1370, 1024, generator=g), torch.randn(1, 128, 2304, generator=g))
+    _check_fwd_bwd(cfg, sd, torch.randn(2, 257, 1024, generator=g), torch.randn(2, 3, 2304, generator=g))
+    # one token: self-attention over a single key has identically zero dQ / dK, so only the forward and the
+    # input gradient are compared (the weight gradients of w_q / w_k are rounding noise around 0 on both sides)
+    vision, text = torch.randn(2, 257, 1024, generator=g), torch.randn(2, 1, 2304, generator=g)
+    y_ref, loss_ref, dtext_ref, g_ref = O.bridge_loss_and_grads(sd, vision, text)
+    m = _make(cfg, sd).eval()
+    t = text.cuda().requires_grad_()
+    y = m(vision.cuda(), t)
+    y.float().square().mean().backward()
+    assert _maxrel(y.detach(), y_ref) <= 2e-2
+    assert _frorel(t.grad, dtext_ref, 1e-2 * float(dtext_ref.norm())) <= 2e-2
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters())
+    w = "bridge_blocks.1.ffn.3.weight"
+    assert _grad_err(dict(m.named_parameters())[w].grad, g_ref[w], 1e-6)[1] <= 3e-2
+
+
+def test_training_mode_dropout_is_unbiased_and_reproducible_in_backward():
+    """dropout (p = 0.1, train mode): the output averaged over many masks approaches the eval output, and
+    the backward regenerates the forward's masks (a gradient computed twice from one forward's state,
+    via retain_graph, is identical; two forwards draw different masks)."""
+    from vlm_bridge_b200 import BridgeLite
+
+    cfg = dict(vision_dim=64, language_dim=128, num_blocks=2, num_heads_cross=2, num_heads_self=1)
+    torch.manual_seed(3)
+    m = BridgeLite(dropout=0.1, **cfg).cuda()
+    g = torch.Generator().manual_seed(9)
+    vision = torch.randn(4, 33, 64, generator=g).cuda()
+    text = torch.randn(4, 24, 128, generator=g).cuda()
+    m.eval()
+    with torch.no_grad():
+        y_eval = m(vision, text)
+    m.train()
+    with torch.no_grad():
+        ys = torch.stack([m(vision, text) for _ in range(200)])
+    assert not torch.equal(ys[0], ys[1])
+    bias = float((ys.mean(0) - y_eval).abs().max() / y_eval.abs().max())
+    spread = float(ys.std(0).max() / y_eval.abs().max())
+    assert bias < 0.05 and spread > 1e-3, (bias, spread)
+    t = text.clone().requires_grad_()
+    y = m(vision, t)
+    (g1,) = torch.autograd.grad(y.square().mean(), t, retain_graph=True)
+    (g2,) = torch.autograd.grad(y.square().mean(), t)
+    assert torch.equal(g1, g2)

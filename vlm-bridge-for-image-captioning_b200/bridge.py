@@ -255,8 +255,8 @@ class _BridgeFunction(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, d_out: torch.Tensor):
         module: BridgeLite = ctx.module
+        # the saved activations stay with ctx (freed with the graph), so backward(retain_graph=True) works
         d_text, grads = module._run_backward(ctx.state, d_out, ctx.text_needs_grad)
-        ctx.state = None
         return (None, None, d_text, *grads)
 
 
