@@ -1,6 +1,7 @@
 // Process-wide state of libb200_bridge.so: last-error string, launch counter, device checks.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -52,6 +53,11 @@ int check_launch(const char* what, cudaStream_t stream) {
     }
   }
   return B200B_OK;
+}
+
+int pdl_mask() {
+  static const int mask = [] { const char* e = getenv("B200B_PDL"); return e ? atoi(e) : 7; }();
+  return mask;
 }
 
 int device_sm_count(int* out) {

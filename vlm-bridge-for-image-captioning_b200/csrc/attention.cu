@@ -162,6 +162,7 @@ __device__ __forceinline__ void store_rows_bf16(const float (&acc)[HD / 8][4], f
 // ================================================================================================
 template <int HD>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
+  pdl_prologue();
   const DropoutCfg drop = dropout_resolve(p.drop);
   using Cfg = AttnCfg<HD>;
   constexpr int BN = Cfg::kBN, kLd = Cfg::kLd;
@@ -319,6 +320,7 @@ __device__ __forceinline__ void pair_barrier(int pair) {
 
 template <int HD, bool PACKED>
 __global__ void __launch_bounds__(256, 2) attn_decode_kernel(const AttnParams p) {
+  pdl_prologue();
   using Cfg = DecodeCfg<HD>;
   constexpr int kLd = Cfg::kLd, TK = Cfg::kTile;
   constexpr int KH = HD / 32;    // 16-wide k-steps of Q K^T per warp (half of the head dim)
@@ -592,6 +594,7 @@ __global__ void __launch_bounds__(256, 2) attn_decode_kernel(const AttnParams p)
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo,
                                   const __nv_bfloat16* __restrict__ d_o, long long lddo, float* __restrict__ delta,
                                   int B, int H, int Lq, int HD) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = blockIdx.x;  // b * Lq + i
   if (warp >= H) return;
@@ -614,6 +617,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long
 // ================================================================================================
 template <int HD>
 __global__ void __launch_bounds__(128) attn_bwd_q_kernel(const AttnParams p) {
+  pdl_prologue();
   const DropoutCfg drop = dropout_resolve(p.drop);
   using Cfg = AttnCfg<HD>;
   constexpr int BN = Cfg::kBN, kLd = Cfg::kLd;
@@ -727,6 +731,7 @@ __global__ void __launch_bounds__(128) attn_bwd_q_kernel(const AttnParams p) {
 // ================================================================================================
 template <int HD>
 __global__ void __launch_bounds__(128) attn_bwd_kv_kernel(const AttnParams p) {
+  pdl_prologue();
   using Cfg = AttnCfg<HD>;
   constexpr int QT = Cfg::kQT, kLd = Cfg::kLd, SL = Cfg::kScrLd;
   extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -847,7 +852,7 @@ static int launch_fwd(const AttnParams& p, cudaStream_t stream) {
   int rc = set_smem(attn_fwd_kernel<HD>, Cfg::kFwdSmem, "attn_fwd");
   if (rc) return rc;
   dim3 grid((p.Lq + Cfg::kBM - 1) / Cfg::kBM, p.H, p.B);
-  attn_fwd_kernel<HD><<<grid, 128, Cfg::kFwdSmem, stream>>>(p);
+  launch_pdl(kPdlAttn, attn_fwd_kernel<HD>, grid, dim3(128), Cfg::kFwdSmem, stream, p);
   return check_launch("attn_fwd", stream);
 }
 
@@ -869,7 +874,7 @@ static int launch_decode(const AttnParams& p, cudaStream_t stream) {
   static const int dbg = [] { const char* e = getenv("B200B_DECODE_DEBUG"); return e ? atoi(e) : 0; }();
   AttnParams pp = p;
   if (dbg & 1) pp.Lkp = -1;
-  attn_decode_kernel<HD, PACKED><<<grid, 256, Cfg::smem_bytes(nrg), stream>>>(pp);
+  launch_pdl(kPdlAttn, attn_decode_kernel<HD, PACKED>, grid, dim3(256), Cfg::smem_bytes(nrg), stream, pp);
   return check_launch(PACKED ? "attn_decode_packed" : "attn_decode", stream);
 }
 
@@ -881,15 +886,16 @@ static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
   rc = set_smem(attn_bwd_kv_kernel<HD>, Cfg::kBwdKVSmem, "attn_bwd_kv");
   if (rc) return rc;
   const int delta_threads = 32 * p.H;
-  attn_delta_kernel<<<p.B * p.Lq, delta_threads, 0, stream>>>(p.o, p.ldo, p.d_o, p.lddo, p.delta, p.B, p.H, p.Lq, HD);
+  launch_pdl(kPdlAttn, attn_delta_kernel, dim3(p.B * p.Lq), dim3(delta_threads), 0, stream, p.o, p.ldo, p.d_o, p.lddo, p.delta, p.B, p.H, p.Lq,
+             HD);
   rc = check_launch("attn_delta", stream);
   if (rc) return rc;
   dim3 gq((p.Lq + Cfg::kBM - 1) / Cfg::kBM, p.H, p.B);
-  attn_bwd_q_kernel<HD><<<gq, 128, Cfg::kBwdQSmem, stream>>>(p);
+  launch_pdl(kPdlAttn, attn_bwd_q_kernel<HD>, gq, dim3(128), Cfg::kBwdQSmem, stream, p);
   rc = check_launch("attn_bwd_q", stream);
   if (rc) return rc;
   dim3 gk((p.Lk + 31) / 32, p.H, p.B);
-  attn_bwd_kv_kernel<HD><<<gk, 128, Cfg::kBwdKVSmem, stream>>>(p);
+  launch_pdl(kPdlAttn, attn_bwd_kv_kernel<HD>, gk, dim3(128), Cfg::kBwdKVSmem, stream, p);
   return check_launch("attn_bwd_kv", stream);
 }
 
@@ -1014,6 +1020,7 @@ namespace b200b {
 // the decode kernel, so that a 16-key tile is ONE contiguous copy that lands bank-conflict free.
 __global__ void kv_cache_pack_kernel(const __nv_bfloat16* __restrict__ kv, long long ldkv,
                                      __nv_bfloat16* __restrict__ packed, int B, int Lk, int H, int HD, int nb) {
+  pdl_prologue();
   const int chunks = (HD + 8) / 8;  // 16-byte chunks per padded row
   const long long total = (long long)B * nb * H * 2 * Lk * chunks;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -1049,9 +1056,8 @@ extern "C" int b200b_kv_cache_pack(const void* kv, int64_t ldkv, void* packed, i
   const long long total = (long long)batch * num_blocks * heads * 2 * len_k * ((head_dim + 8) / 8);
   const int threads = 256;
   const int blocks = (int)((total + threads - 1) / threads < 148 * 16 ? (total + threads - 1) / threads : 148 * 16);
-  kv_cache_pack_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(kv), ldkv,
-                                                       reinterpret_cast<__nv_bfloat16*>(packed), batch, len_k, heads,
-                                                       head_dim, num_blocks);
+  launch_pdl(kPdlAttn, kv_cache_pack_kernel, dim3(blocks), dim3(threads), 0, stream, reinterpret_cast<const __nv_bfloat16*>(kv),
+             (long long)ldkv, reinterpret_cast<__nv_bfloat16*>(packed), batch, len_k, heads, head_dim, num_blocks);
   return check_launch("kv_cache_pack", stream);
 }
 

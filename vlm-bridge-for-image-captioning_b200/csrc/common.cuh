@@ -131,6 +131,26 @@ __device__ __forceinline__ bool dropout_keep(const uint4& bits, int e /*0..7*/, 
 }
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch: a kernel launched with launch_pdl() (launch.h) may become resident
+// while its predecessor on the stream is still running. pdl_launch_dependents() lets the NEXT kernel
+// do that once every CTA of this one has reached the call; pdl_wait() blocks until the predecessor
+// grid has completed and its memory is visible -- nothing before it may touch global memory that an
+// earlier kernel writes or reads.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+// For kernels whose CTAs can be co-resident with a persistent GEMM: they wait, but do not let THEIR
+// dependents start early (the implicit trigger at exit applies), so at most one level of look-ahead
+// passes through them.
+__device__ __forceinline__ void pdl_prologue_late_trigger() { pdl_wait(); }
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

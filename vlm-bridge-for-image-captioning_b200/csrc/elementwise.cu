@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16
                                                              const float* __restrict__ rstd, float* __restrict__ psum,
                                                              float* __restrict__ pgsum, int rows, int cols,
                                                              int rows_per_chunk) {
+  pdl_prologue_late_trigger();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = (blockIdx.x * 32 + tx) * 4;
   const int r0 = blockIdx.y * rows_per_chunk;
@@ -197,6 +198,7 @@ static int colsum_chunks(int rows, int cols, int num_sms) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                         long long n8, DropoutCfg drop_in, uint32_t stream) {
+  pdl_prologue_late_trigger();
   const DropoutCfg drop = dropout_resolve(drop_in);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n8; g += stride) {
@@ -249,6 +251,7 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_fwd_row_kernel(const fl
                                                                         float* __restrict__ mean_out,
                                                                         float* __restrict__ rstd_out, int rows,
                                                                         int dim, float eps) {
+  pdl_prologue_late_trigger();
   __shared__ float2 red[4][kRowThreads / 32];
   float4 g[VPT], b[VPT];
 #pragma unroll
@@ -336,6 +339,7 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_bwd_row_kernel(
     const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean_in,
     const float* __restrict__ rstd_in, const float* __restrict__ gamma, const float* dres, float* dx,
     __nv_bfloat16* __restrict__ dy_next, float* __restrict__ partials, int rows, int dim) {
+  pdl_prologue_late_trigger();
   __shared__ float2 red[2][kRowThreads / 32];
   float4 gm[VPT], pb[VPT], pg[VPT], pc[VPT];
 #pragma unroll
@@ -417,6 +421,7 @@ __global__ void __launch_bounds__(288) cast_colsum_row_kernel(const float* __res
                                                               __nv_bfloat16* __restrict__ out,
                                                               float* __restrict__ partials, int rows, int dim,
                                                               DropoutCfg drop_in, uint32_t stream) {
+  pdl_prologue_late_trigger();
   const DropoutCfg drop = dropout_resolve(drop_in);
   float ps[GPT][8];
 #pragma unroll
@@ -469,6 +474,7 @@ struct FinalizeTasks {
 // independent 16-byte loads in flight, then the 8 lanes are combined through shared memory in a
 // fixed order (deterministic).
 __global__ void __launch_bounds__(256) colsum_finalize_multi_kernel(const FinalizeTasks tasks) {
+  pdl_prologue_late_trigger();
   const b200b_colsum_task& t = tasks.t[blockIdx.y];
   if (blockIdx.x * 128 >= t.cols) return;  // whole block out of range for this (shorter) task
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -503,6 +509,7 @@ __global__ void __launch_bounds__(256) colsum_finalize_multi_kernel(const Finali
 // out f32 = scale * in bf16 (exchanged gradient bucket -> .grad)
 __global__ void __launch_bounds__(256) bf16_to_f32_kernel(const uint4* __restrict__ in, float4* __restrict__ out,
                                                           long long n8, float scale) {
+  pdl_prologue_late_trigger();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n8; g += stride) {
     const uint4 v = __ldcs(in + g);
@@ -626,7 +633,7 @@ extern "C" int b200b_colsum(const void* dy_bf16, int64_t ld, const float* x, con
   float* pgsum = psum + (size_t)chunks * cols;
   const int rows_per_chunk = (rows + chunks - 1) / chunks;
   dim3 grid((cols + 127) / 128, chunks);
-  colsum_partial_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16), (long long)ld, x,
+  launch_pdl(kPdlRows, colsum_partial_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(dy_bf16), (long long)ld, x,
                                                   mean, rstd, psum, pgsum, rows, cols, rows_per_chunk);
   rc = check_launch("colsum_partial", stream);
   if (rc != B200B_OK) return rc;
@@ -662,7 +669,7 @@ extern "C" int b200b_cast_bf16(const float* in, void* out_bf16, int64_t n, float
   const long long cap = (long long)num_sms * 8;  // 8 resident CTAs of 256 threads per SM, grid-stride beyond
   if (blocks > cap) blocks = cap;
   const DropoutCfg dc = make_dropout_cfg(dropout_p, seed, &dropout_stream);
-  cast_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out_bf16), n8, dc,
+  launch_pdl(kPdlRows, cast_bf16_kernel, dim3((int)blocks), dim3(256), 0, stream, in, reinterpret_cast<__nv_bfloat16*>(out_bf16), n8, dc,
                                                     dropout_stream);
   return check_launch("cast_bf16", stream);
 }
@@ -710,7 +717,7 @@ extern "C" int b200b_layernorm_fwd_rows(const float* x, const float* gamma, cons
   if (rc != B200B_OK) return rc;
   const int grid = rows < 8 * num_sms ? rows : 8 * num_sms;
 #define CALL(V)                                                                                                   \
-  layernorm_fwd_row_kernel<V><<<grid, kRowThreads, 0, stream>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), \
+  launch_pdl(kPdlRows, layernorm_fwd_row_kernel<V>, dim3(grid), dim3(kRowThreads), 0, stream, x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), \
                                                                 mean, rstd, rows, dim, eps)
   B200B_DISPATCH_VPT(dim, CALL);
 #undef CALL
@@ -741,7 +748,7 @@ extern "C" int b200b_layernorm_bwd_fused(const void* dy_bf16, const float* x, co
   const int grid = b200b_row_chunks(rows);
   if (grid <= 0) return B200B_ERR_DEVICE;
 #define CALL(V)                                                                                              \
-  layernorm_bwd_row_kernel<V><<<grid, kRowThreads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16), x, mean, \
+  launch_pdl(kPdlRows, layernorm_bwd_row_kernel<V>, dim3(grid), dim3(kRowThreads), 0, stream, reinterpret_cast<const __nv_bfloat16*>(dy_bf16), x, mean, \
                                                                 rstd, gamma, dres, dx,                       \
                                                                 reinterpret_cast<__nv_bfloat16*>(dy_next_bf16), partials, rows, dim)
   B200B_DISPATCH_VPT(dim, CALL);
@@ -773,9 +780,9 @@ extern "C" int b200b_cast_bf16_colsum(const float* in, void* out_bf16, float* pa
   const DropoutCfg dc = make_dropout_cfg(dropout_p, seed, &dropout_stream);
   const int gpt = (dim / 8 + 287) / 288;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  if (gpt <= 1) cast_colsum_row_kernel<1><<<grid, 288, 0, stream>>>(in, o, partials, rows, dim, dc, dropout_stream);
-  else if (gpt <= 2) cast_colsum_row_kernel<2><<<grid, 288, 0, stream>>>(in, o, partials, rows, dim, dc, dropout_stream);
-  else cast_colsum_row_kernel<4><<<grid, 288, 0, stream>>>(in, o, partials, rows, dim, dc, dropout_stream);
+  if (gpt <= 1) launch_pdl(kPdlRows, cast_colsum_row_kernel<1>, dim3(grid), dim3(288), 0, stream, in, o, partials, rows, dim, dc, dropout_stream);
+  else if (gpt <= 2) launch_pdl(kPdlRows, cast_colsum_row_kernel<2>, dim3(grid), dim3(288), 0, stream, in, o, partials, rows, dim, dc, dropout_stream);
+  else launch_pdl(kPdlRows, cast_colsum_row_kernel<4>, dim3(grid), dim3(288), 0, stream, in, o, partials, rows, dim, dc, dropout_stream);
   return check_launch("cast_colsum", stream);
 }
 
@@ -800,7 +807,7 @@ extern "C" int b200b_colsum_partials(const void* dy_bf16, int64_t ld, int rows, 
   const int chunks = colsum_chunks(rows, cols, num_sms);
   const int rows_per_chunk = (rows + chunks - 1) / chunks;
   dim3 grid((cols + 127) / 128, chunks);
-  colsum_partial_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_bf16), (long long)ld, nullptr,
+  launch_pdl(kPdlRows, colsum_partial_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(dy_bf16), (long long)ld, nullptr,
                                                   nullptr, nullptr, partials, nullptr, rows, cols, rows_per_chunk);
   *chunks_out = chunks;
   return check_launch("colsum_partial", stream);
@@ -825,7 +832,7 @@ extern "C" int b200b_colsum_finalize(const b200b_colsum_task* tasks, int ntasks,
     if (tasks[i].cols > max_cols) max_cols = tasks[i].cols;
   }
   dim3 grid((max_cols + 127) / 128, ntasks);
-  colsum_finalize_multi_kernel<<<grid, 256, 0, stream>>>(ft);
+  launch_pdl(kPdlRows, colsum_finalize_multi_kernel, dim3(grid), dim3(256), 0, stream, ft);
   return check_launch("colsum_final", stream);
 }
 
@@ -850,7 +857,7 @@ extern "C" int b200b_bf16_to_f32(const void* in_bf16, float* out, int64_t n, flo
   long long blocks = (n8 + 255) / 256;
   const long long cap = (long long)num_sms * 8;
   if (blocks > cap) blocks = cap;
-  bf16_to_f32_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(in_bf16),
+  launch_pdl(kPdlRows, bf16_to_f32_kernel, dim3((int)blocks), dim3(256), 0, stream, reinterpret_cast<const uint4*>(in_bf16),
                                                       reinterpret_cast<float4*>(out), n8, scale);
   return check_launch("bf16_to_f32", stream);
 }

@@ -338,6 +338,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t tmem_base = tmem_base_smem;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
 
@@ -516,6 +518,9 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   tc_fence_before();
   cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / TMA credit
   tc_fence_after();
+  // everything above is CTA-local set-up; it may overlap the tail of the previous kernel on the stream
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t tmem_base = tmem_base_smem;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;  // num_m_blocks counts 256-row pair tiles
 
@@ -673,7 +678,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
       }
       configured = true;
     }
-    kern<<<grid, kGemmThreads, GemmPairCfg<BLOCK_N>::kSmemBytes, stream>>>(ta, tb, p);
+    launch_pdl(kPdlGemm, kern, dim3(grid), dim3(kGemmThreads), GemmPairCfg<BLOCK_N>::kSmemBytes, stream, ta, tb, p);
     return check_launch("gemm_tcgen05_pair_kernel", stream);
   } else {
     auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI>;
@@ -686,7 +691,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
       }
       configured = true;
     }
-    kern<<<grid, kGemmThreads, GemmCfg<BLOCK_N>::kSmemBytes, stream>>>(ta, tb, p);
+    launch_pdl(kPdlGemm, kern, dim3(grid), dim3(kGemmThreads), GemmCfg<BLOCK_N>::kSmemBytes, stream, ta, tb, p);
     return check_launch("gemm_tcgen05_kernel", stream);
   }
 }

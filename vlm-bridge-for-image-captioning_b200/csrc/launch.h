@@ -16,6 +16,31 @@ int check_launch(const char* what, cudaStream_t stream);
 // SM count of the current device (cached per device); fails on non-sm_100 devices
 int device_sm_count(int* out);
 
+// Which kernel families are launched with programmatic stream serialization: bit mask from the
+// environment variable B200B_PDL (1 = GEMMs, 2 = attention, 4 = row / column / cast kernels).
+enum { kPdlGemm = 1, kPdlAttn = 2, kPdlRows = 4 };
+int pdl_mask();
+
+// Launch `kern` so that it may be scheduled while the previous kernel on `stream` is still running
+// (programmatic dependent launch; also captured as a programmatic edge in CUDA graphs) when `family`
+// is enabled. Only for kernels that call pdl_wait() / pdl_prologue() before their first
+// global-memory access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int family, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_mask() & family) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // `stream` is the caller's dropout stream id: its B200B_SEED_INDIRECT bit says that `seed` is a device
 // pointer to the 64-bit seed; the bit is cleared from `stream` here.
 inline DropoutCfg make_dropout_cfg(float p, uint64_t seed, uint32_t* stream) {
