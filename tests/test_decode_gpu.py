@@ -65,6 +65,9 @@ def test_greedy_decode_matches_oracle_and_is_sync_free_batched():
     ids_nc, _ = greedy_decode(m, vision.cuda(), lambda t: embed_d[t], lambda h: h[:, -1, :] @ head_d.t(),
                               bos_token_id=2, eos_token_id=1, max_new_tokens=steps, use_cache=False)
     assert torch.equal(ids, ids_nc)                      # cache on / off: identical token ids
+    ids_g, _ = greedy_decode(m, vision.cuda(), lambda t: embed_d[t], lambda h: h[:, -1, :] @ head_d.t(),
+                             bos_token_id=2, eos_token_id=1, max_new_tokens=steps, use_graphs=True)
+    assert torch.equal(ids, ids_g)                       # one graph replay per prefix length: identical
     assert ids.shape == (B, steps + 1) and bool((ids[:, 0] == 2).all())
     # teacher-forced comparison with the fp32 oracle on the CUDA path's own prefixes
     ids_c = ids.cpu()

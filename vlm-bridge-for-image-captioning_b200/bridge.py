@@ -287,6 +287,7 @@ class BridgeLite(nn.Module):
         # data-parallel reducer (parallel.GradBucketReducer) driven by _run_backward
         self._bucket_hook = None
         self._last_grad_arena: Optional[torch.Tensor] = None
+        self._graph_recast = True
 
     # -- init exactly as the reference (bridge_module.py:394-404) ---------------------------------
     def _init_weights(self) -> None:
@@ -363,8 +364,9 @@ class BridgeLite(nn.Module):
     def _refresh_bf16(self) -> None:
         key = tuple(p._version for _, p in self._named_params())
         # while a CUDA graph is being captured the cast is always recorded: the optimizer updates the
-        # fp32 masters between replays without this code running again
-        if key == self._w16_key and not torch.cuda.is_current_stream_capturing():
+        # fp32 masters between replays without this code running again (inference graphs, whose weights
+        # are frozen for the graph's lifetime, opt out through `_graph_recast`)
+        if key == self._w16_key and not (torch.cuda.is_current_stream_capturing() and self._graph_recast):
             return
         lay = self._layout
         _lib.check(_lib.lib().b200b_cast_bf16(self._flat.data_ptr(), self._w16.data_ptr(), lay.n_weights, 0.0, 0, 0,

@@ -25,17 +25,60 @@ import torch
 
 from .kv_cache import VisionKVCache
 
-__all__ = ["greedy_decode"]
+__all__ = ["greedy_decode", "DecodeStepGraphs"]
+
+
+class DecodeStepGraphs:
+    """One captured CUDA graph of the bridge forward per (batch, prefix length), over a fixed
+    `VisionKVCache`: a decode step is ~45 short kernels, so enqueueing them from Python takes longer
+    than they run; a replay costs one launch. The graphs share a memory pool (they never run
+    concurrently) and are valid while the cache is (`VisionKVCache.is_current()`); the bf16 weight
+    copies are NOT re-cast inside these graphs (inference: the weights are frozen)."""
+
+    def __init__(self, bridge, kv_cache: VisionKVCache):
+        self.bridge, self.cache = bridge, kv_cache
+        self._graphs: dict = {}
+        self._pool = None
+
+    def __call__(self, text_embeddings: torch.Tensor) -> torch.Tensor:
+        """bridge(vision, text_embeddings, kv_cache=cache) for text_embeddings [B, s, D]; the returned
+        tensor is the graph's static output (overwritten by the next call with the same shape)."""
+        if not self.cache.is_current():
+            raise RuntimeError("the K/V cache is stale (bridge weights changed): rebuild it and the graphs")
+        key = (int(text_embeddings.shape[0]), int(text_embeddings.shape[1]))
+        ent = self._graphs.get(key)
+        if ent is None:
+            b = self.bridge
+            static_in = text_embeddings.detach().to(torch.float32).clone()
+            with torch.no_grad():
+                b(None, static_in, kv_cache=self.cache)           # lazy initialisation outside the capture
+                torch.cuda.synchronize()
+                if self._pool is None:
+                    self._pool = torch.cuda.graph_pool_handle()
+                g = torch.cuda.CUDAGraph()
+                recast, b._graph_recast = b._graph_recast, False
+                try:
+                    with torch.cuda.graph(g, pool=self._pool):
+                        out = b(None, static_in, kv_cache=self.cache)
+                finally:
+                    b._graph_recast = recast
+            ent = self._graphs[key] = (g, static_in, out)
+        g, static_in, out = ent
+        static_in.copy_(text_embeddings, non_blocking=True)
+        g.replay()
+        return out
 
 
 @torch.no_grad()
 def greedy_decode(bridge, vision_features: torch.Tensor, embed_fn: Callable[[torch.Tensor], torch.Tensor],
                   lm_fn: Callable[[torch.Tensor], torch.Tensor], *, bos_token_id: int,
                   eos_token_id: Optional[int] = None, max_new_tokens: int = 50,
-                  kv_cache: Optional[VisionKVCache] = None, use_cache: bool = True):
+                  kv_cache: Optional[VisionKVCache] = None, use_cache: bool = True,
+                  step_graphs: Optional[DecodeStepGraphs] = None, use_graphs: bool = False):
     """Returns (ids [B, 1 + max_new_tokens] int64 incl. BOS, lengths [B] int64): row b's caption is
     ids[b, 1:lengths[b]] (EOS excluded); positions from lengths[b] on are what the lock-step loop kept
-    generating and are to be ignored."""
+    generating and are to be ignored. `use_graphs` replays one captured CUDA graph of the bridge per
+    prefix length (`DecodeStepGraphs`; pass `step_graphs` to reuse graphs captured for the same cache)."""
     was_training = bridge.training
     bridge.eval()
     try:
@@ -43,11 +86,19 @@ def greedy_decode(bridge, vision_features: torch.Tensor, embed_fn: Callable[[tor
         dev = vision_features.device
         if use_cache and kv_cache is None:
             kv_cache = VisionKVCache(bridge, vision_features)
+        if (use_graphs or step_graphs is not None) and use_cache:
+            if step_graphs is None or step_graphs.cache is not kv_cache:
+                step_graphs = DecodeStepGraphs(bridge, kv_cache)
+        else:
+            step_graphs = None
         ids = torch.empty((B, 1 + max_new_tokens), dtype=torch.long, device=dev)
         ids[:, 0] = bos_token_id
         for step in range(max_new_tokens):
             prefix = ids[:, :step + 1]
-            hidden = bridge(vision_features, embed_fn(prefix), kv_cache=kv_cache if use_cache else None)
+            if step_graphs is not None:
+                hidden = step_graphs(embed_fn(prefix))
+            else:
+                hidden = bridge(vision_features, embed_fn(prefix), kv_cache=kv_cache if use_cache else None)
             logits = lm_fn(hidden)
             if logits.dim() == 3:
                 logits = logits[:, -1, :]
