@@ -245,6 +245,7 @@ def run_b200_arm(args) -> int:
                              backend=args.dp_backend, nvls_blocks=args.nvls_blocks, nvls_threads=args.nvls_threads,
                              bucket_bytes=args.bucket_mb << 20, exclusive_sms=args.nvls_exclusive,
                              fp32_multicast=args.nvls_fp32_multicast)
+        model._bucket_hook.diag_skip_convert = args.diag_dp_skip_convert
 
     def step(v, t):
         model._w16_key = None            # weights count as updated by the optimizer since last step
@@ -672,6 +673,8 @@ def main() -> int:
     ap.add_argument("--nvls-threads", type=int, default=512)
     ap.add_argument("--nvls-exclusive", action="store_true", help="reserve --nvls-blocks SMs for the exchange")
     ap.add_argument("--nvls-fp32-multicast", action="store_true", help="broadcast fp32 into .grad (no conversion pass)")
+    ap.add_argument("--diag-dp-skip-convert", action="store_true",
+                    help="diagnostics: skip the bf16 -> fp32 pass of the exchange (gradients are then incomplete)")
     ap.add_argument("--bucket-mb", type=int, default=32)
     ap.add_argument("--grad-dtype", default="bf16", choices=["bf16", "f32"],
                     help="dtype of the data-parallel weight-gradient exchange (N > 1)")

@@ -65,6 +65,7 @@ class GradBucketReducer:
         self.nvls_threads = int(nvls_threads)
         self.exclusive_sms = bool(exclusive_sms) and self.nvls_blocks % 2 == 0
         self.fp32_multicast = bool(fp32_multicast)   # False: bf16 result in place + a separate bf16 -> fp32 pass
+        self.diag_skip_convert = False  # diagnostics only: leaves .grad of the weights unwritten (timing what the pass costs)
         self._nvls = None               # (comm struct, symmetric byte buffer, flag buffer, handles)
         self.trace: Optional[list] = None   # set to [] to record per-bucket CUDA events (diagnostics)
         self._t0 = None
@@ -244,8 +245,9 @@ class GradBucketReducer:
                     from . import _lib
 
                     self._launch_nvls(nv["off16"] + 2 * lo, nbytes, True)
-                    _lib.check(_lib.lib().b200b_bf16_to_f32(chunk.data_ptr(), self._arena32[lo:hi].data_ptr(), hi - lo,
-                                                            1.0, self._post.cuda_stream), "bf16_to_f32")
+                    if not self.diag_skip_convert:
+                        _lib.check(_lib.lib().b200b_bf16_to_f32(chunk.data_ptr(), self._arena32[lo:hi].data_ptr(), hi - lo,
+                                                                1.0, self._post.cuda_stream), "bf16_to_f32")
             if self.trace is not None:
                 self.trace[-1][3][2].record(self._post)
             return
