@@ -636,7 +636,7 @@ def bench_decode(model, dev, peaks, _lib) -> dict:
     loop(cache)
     entries = _lib.profile_end()
     # cross-attention launches over the cached K/V: the packed-layout decode kernel
-    cross_ms = sum(ms_ for name, ms_ in entries if name == "attn_decode_packed")
+    cross_ms = sum(ms_ for name, ms_ in entries if name in ("attn_decode_packed", "attn_decode_tc"))
     bytes_total = sum(decode_bytes_per_step(DEC_B, s, N_VIS) for s in range(1, DEC_STEPS + 1))
     achieved = bytes_total / (cross_ms * 1e-3) / 1e9 if cross_ms > 0 else 0.0
     return {
@@ -646,12 +646,13 @@ def bench_decode(model, dev, peaks, _lib) -> dict:
                                                 "graph replay per prefix length (cache and graphs reused)": ms_graph},
         "uncached_tokens_per_s": DEC_B * DEC_STEPS / (ms_uncached * 1e-3),
         "config": f"C4: batch {DEC_B}, {DEC_STEPS} new tokens, prefix recomputed every step (non-causal bridge), Nv={N_VIS}",
-        "roofline": {"bound": "hbm", "kernel": "attn_decode_kernel<288, packed> (the 128 cross-attention launches)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": "attn_decode_kernel<288, packed> for <= 32 positions, attn_decode_tc_kernel<288> above (the 128 cross-attention launches)", "achieved": achieved,
                      "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": None,
                      "algorithmic_bytes_total": bytes_total, "kernel_ms_total": cross_ms,
-                     "note": ("event-timed between eager launches; s > 16 query rows is bound by the legacy HMMA pipe "
-                              "(mma.sync peaks near 144 TF/s on B200), s <= 16 runs at ~65 % of the HBM peak "
-                              "(profiles/r01_exp_decode_v3.jsonl)")},
+                     "note": ("event-timed between eager launches. Graph-timed per launch (profiles/r01_exp_decode_v3.jsonl, "
+                              "r01_exp_decode_tc_v4.jsonl): 17-19 us (65-68 % of the HBM peak) up to 16 positions, 24-25 us up to 32 "
+                              "(legacy HMMA pipe), 28-31 us (47 %) for 33-64 on the tcgen05 kernel, whose M=64 MMAs cost >= 47 "
+                              "cycles each on the tensor pipe whatever their size")},
         "kv_cache_bytes": cache.nbytes,
     }
 

@@ -213,6 +213,18 @@ int b200b_attention_decode_packed(const void* q, int64_t ldq, const void* kv_pac
                                   int num_blocks, void* o, int64_t ldo, float* lse, int batch, int heads,
                                   int len_q, int len_k, int head_dim, void* stream);
 
+/* The same decode step on the tcgen05 tensor cores (csrc/attention_tc.cu): the mma.sync kernel above is
+ * bound by the legacy tensor pipe beyond 16 query rows. b200b_kv_cache_pack_tc stores, per (image, block,
+ * head), 64-key tiles (the last padded to a multiple of 16 keys) as the shared-memory images the MMAs read
+ * (K tile [d/16][keys][32 B], then V^T tile [keys/16][d][32 B], 32-byte swizzle), so a tile is one
+ * contiguous TMA bulk copy; b200b_attention_decode_tc is b200b_attention_decode_packed on that layout. */
+size_t b200b_kv_cache_tc_bytes(int batch, int len_k, int heads, int head_dim, int num_blocks);
+int b200b_kv_cache_pack_tc(const void* kv, int64_t ldkv, void* packed, int batch, int len_k, int heads,
+                           int head_dim, int num_blocks, void* stream);
+int b200b_attention_decode_tc(const void* q, int64_t ldq, const void* kv_tc, int block_index, int num_blocks,
+                              void* o, int64_t ldo, float* lse, int batch, int heads, int len_q, int len_k,
+                              int head_dim, void* stream);
+
 /* ------------------------------------------------------------------------------------------- *
  * Whole-block entry points: one call enqueues every kernel of a BridgeBlock forward or backward
  * (reference: BridgeBlock.forward, bridge_module.py:300-335, and the autograd graph it builds).
@@ -242,6 +254,9 @@ typedef struct b200b_bridge_dims {
 /* flags (block_forward only): `kv` is the packed decode cache written by b200b_kv_cache_pack, not the
  * row-major projection output. Needs dropout_p == 0 and len_text <= 64. */
 #define B200B_BRIDGE_KV_PACKED 4
+/* flags (block_forward only): `kv` is the tcgen05 decode cache written by b200b_kv_cache_pack_tc; the
+ * cross-attention runs b200b_attention_decode_tc. Same conditions as B200B_BRIDGE_KV_PACKED. */
+#define B200B_BRIDGE_KV_TC 8
 /* The same for the individual operators: OR this bit into `dropout_stream` and pass the device
  * pointer (cast to uint64_t) as `seed`. */
 #define B200B_SEED_INDIRECT 0x80000000u
@@ -395,6 +410,15 @@ int b200b_allreduce_nvls(const b200b_nvls_comm* comm, int dtype, int64_t byte_of
  * statically scheduled GEMM CTAs never share (or wait for) an SM with an exchange CTA. Process-wide. */
 void b200b_set_sm_limit(int sms);
 int b200b_get_sm_limit(void);
+
+/* Diagnostic, not part of the bridge path (csrc/probe_tcgen05.cu): one CTA computes a[m,k] b[n,k]^T with
+ * tcgen05.mma on operands it lays out in shared memory with the given swizzle width (32 / 64 / 128 bytes,
+ * K-major) and dumps all 128 TMEM lanes x n columns of the accumulator to `dump` (fp32 [128, n]).
+ * m in {64, 128}; n % 16 == 0, 16 <= n <= 256; k a multiple of swizzle_bytes / 2. With reps > 0 the MMA sequence is
+ * first issued reps times into a scratch accumulator and cycles2[0..1] (device, int64) receive the SM clock cycles spent
+ * issuing and until completion. */
+int b200b_probe_umma(const void* a, const void* b, float* dump, int m, int n, int k, int swizzle_bytes,
+                     int reps, long long* cycles2, void* stream);
 
 #ifdef __cplusplus
 }

@@ -6,7 +6,9 @@ replaced by a fixed embedding table and a fixed linear read-out, so the loop
 (embed prefix -> bridge -> logits of the last position -> argmax -> append) is the reference's
 (full_model.py:241-363) with the bridge as the only arithmetic under test.
 
-Tolerances: cached vs uncached bridge output: bit-exact (same kernels' arithmetic in the same order);
+Tolerances: cached vs uncached bridge output: bit-exact up to 32 positions and beyond 64 (same arithmetic in
+the same order); within 5e-3 (relative to the output maximum) for 33..64 positions, where the cache is read by
+the tcgen05 kernel (bf16 probabilities against a lazily updated row maximum instead of the exact one);
 CUDA (bf16 operands, fp32 accumulate) vs fp32 oracle: max|d|/max|ref| <= 2e-2; greedy token ids equal
 to the oracle's wherever the oracle's top-2 logit margin exceeds the bf16 logit error bound
 (2e-2 * max|logit|), which must hold for at least 90 % of the steps.
@@ -43,7 +45,10 @@ def test_cached_forward_is_bit_exact_and_matches_oracle(s):
         y_cached = m(vision.cuda(), text.cuda(), kv_cache=cache)
         y_plain = m(vision.cuda(), text.cuda())
     assert cache.is_current()
-    assert torch.equal(y_cached, y_plain)
+    if s <= 32 or s > 64:
+        assert torch.equal(y_cached, y_plain)      # same arithmetic in the same order (mma.sync kernels)
+    else:                                          # 33..64 positions: the tcgen05 decode kernel
+        assert float((y_cached - y_plain).abs().max() / y_plain.abs().max()) <= 5e-3
     if s in (1, 17, 64):
         y_ref = O.bridge_forward_cached(sd, O.vision_kv(sd, vision), text)
         assert float((y_cached.cpu() - y_ref).abs().max() / y_ref.abs().max()) <= 2e-2
@@ -98,3 +103,29 @@ def test_stale_cache_is_detected():
     with torch.no_grad():
         next(m.parameters()).add_(1e-3)
     assert not cache.is_current()
+
+
+@pytest.mark.parametrize("B,H,HD,Lq,Lk,NB", [(1, 1, 64, 16, 64, 1), (2, 2, 128, 5, 100, 2), (2, 8, 288, 1, 257, 2),
+                                             (3, 8, 288, 17, 257, 2), (2, 8, 288, 64, 257, 2), (1, 8, 288, 40, 16, 1),
+                                             (1, 8, 288, 33, 130, 2), (1, 8, 288, 64, 1370, 2)])
+def test_tcgen05_decode_attention_matches_fp32_reference(B, H, HD, Lq, Lk, NB):
+    """b200b_kv_cache_pack_tc + b200b_attention_decode_tc against softmax(Q K^T / sqrt(d)) V in fp32 torch:
+    output within 1e-2 of the output maximum (bf16 operands and probabilities), log-sum-exp within 1e-3."""
+    import math
+
+    from vlm_bridge_b200 import ops
+
+    g = torch.Generator().manual_seed(B * 1000 + Lq * 10 + Lk)
+    D = H * HD
+    kv = torch.randn(B * Lk, NB * 2 * D, generator=g).bfloat16().cuda()
+    q = torch.randn(B * Lq, D, generator=g).bfloat16().cuda()
+    kvt = ops.kv_cache_pack_tc(kv, batch=B, len_k=Lk, heads=H, head_dim=HD, num_blocks=NB)
+    blk = NB - 1
+    o, lse = ops.attention_decode_tc(q, kvt, block_index=blk, num_blocks=NB, batch=B, heads=H, len_q=Lq, len_k=Lk,
+                                     head_dim=HD)
+    k = kv[:, 2 * D * blk:2 * D * blk + D].float().reshape(B, Lk, H, HD).transpose(1, 2)
+    v = kv[:, 2 * D * blk + D:2 * D * (blk + 1)].float().reshape(B, Lk, H, HD).transpose(1, 2)
+    s = q.float().reshape(B, Lq, H, HD).transpose(1, 2) @ k.transpose(-1, -2) / math.sqrt(HD)
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * Lq, D)
+    assert float((o.float() - ref).abs().max() / ref.abs().max()) <= 1e-2
+    assert float((lse * math.log(2) - torch.logsumexp(s, -1)).abs().max()) <= 1e-3

@@ -139,6 +139,9 @@ def _declare(lib) -> None:
     lib.b200b_adamw_fused.restype = C.c_int
     lib.b200b_adamw_fused.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_int64, C.c_void_p, C.c_float, C.c_void_p,
                                                           C.c_void_p] + [C.c_float] * 5 + [C.c_int64, C.c_void_p]
+    lib.b200b_probe_umma.restype = C.c_int
+    lib.b200b_probe_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p]
     lib.b200b_set_sm_limit.restype = None
     lib.b200b_set_sm_limit.argtypes = [C.c_int]
     lib.b200b_get_sm_limit.restype = C.c_int
@@ -154,6 +157,13 @@ def _declare(lib) -> None:
     lib.b200b_attention_decode_packed.restype = C.c_int
     lib.b200b_attention_decode_packed.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                                   C.c_int64, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
+    lib.b200b_kv_cache_tc_bytes.restype = C.c_size_t
+    lib.b200b_kv_cache_tc_bytes.argtypes = [C.c_int] * 5
+    lib.b200b_kv_cache_pack_tc.restype = C.c_int
+    lib.b200b_kv_cache_pack_tc.argtypes = [C.c_void_p, C.c_int64, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
+    lib.b200b_attention_decode_tc.restype = C.c_int
+    lib.b200b_attention_decode_tc.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                              C.c_int64, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
     lib.b200b_attention_bwd_workspace_bytes.restype = C.c_size_t
     lib.b200b_attention_bwd_workspace_bytes.argtypes = [C.c_int] * 4
     lib.b200b_attention_bwd.restype = C.c_int

@@ -182,6 +182,8 @@ class _BridgeDims(C.Structure):
 FLAG_WGRAD_BF16 = 1      # B200B_BRIDGE_WGRAD_BF16
 FLAG_SEED_INDIRECT = 2   # B200B_BRIDGE_SEED_INDIRECT
 FLAG_KV_PACKED = 4       # B200B_BRIDGE_KV_PACKED
+FLAG_KV_TC = 8           # B200B_BRIDGE_KV_TC
+TC_DECODE_MIN_LEN = 33   # prefix lengths from which the tcgen05 decode kernel beats the mma.sync one (measured)
 _SEED_STRIDE = 0x1E3779B97F4A7C15  # odd 61-bit increment of the device-resident dropout seed
 _GRAD_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int64)
 
@@ -429,6 +431,17 @@ class BridgeLite(nn.Module):
                                            self.num_heads_cross, d, self.num_blocks, _stream()), "kv_cache_pack")
         return packed
 
+    def pack_vision_kv_tc(self, kv: torch.Tensor, batch: int, len_vision: int) -> torch.Tensor:
+        """tcgen05 decode layout of a `project_vision_kv` result (csrc/attention_tc.cu): per image / block /
+        head, 32-key tiles stored as the swizzled shared-memory images the MMAs read."""
+        lib = _bridge_lib()
+        d = self.language_dim // self.num_heads_cross
+        nbytes = lib.b200b_kv_cache_tc_bytes(batch, len_vision, self.num_heads_cross, d, self.num_blocks)
+        packed = torch.empty(nbytes, device=kv.device, dtype=torch.uint8)
+        _lib.check(lib.b200b_kv_cache_pack_tc(kv.data_ptr(), kv.stride(0), packed.data_ptr(), batch, len_vision,
+                                              self.num_heads_cross, d, self.num_blocks, _stream()), "kv_cache_pack_tc")
+        return packed
+
     # -- forward / backward drivers ----------------------------------------------------------------
     def _run_forward(self, vision: torch.Tensor, text: torch.Tensor, keep_for_backward: bool, kv_cache=None,
                      block_callback=None):
@@ -455,8 +468,9 @@ class BridgeLite(nn.Module):
         packed = (kv_cache is not None and not keep_for_backward and L <= 64 and not (self.training and self.dropout_p > 0)
                   and getattr(kv_cache, "kv_packed", None) is not None
                   and (self.language_dim // self.num_heads_cross) in (64, 128, 288))
+        use_tc = packed and L >= TC_DECODE_MIN_LEN and getattr(kv_cache, "kv_tc", None) is not None
         if packed:
-            kv = kv_cache.kv_packed
+            kv = kv_cache.kv_tc if use_tc else kv_cache.kv_packed
         saved_bytes = lib.b200b_bridge_block_saved_bytes(C.byref(dims))
         n_arenas = self.num_blocks if keep_for_backward else 1
         saved = torch.empty(n_arenas * saved_bytes, device=dev, dtype=torch.uint8)
@@ -472,7 +486,7 @@ class BridgeLite(nn.Module):
             else:
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         if packed:
-            dims = self._dims(B, L, Nv, flags | FLAG_KV_PACKED)
+            dims = self._dims(B, L, Nv, flags | (FLAG_KV_TC if use_tc else FLAG_KV_PACKED))
         ptrs = self._weight_ptrs()
         xs = [x.view(B * L, D)]
         st = _stream()

@@ -236,12 +236,15 @@ extern "C" int b200b_bridge_block_forward(const b200b_bridge_dims* dims, int i, 
   B200B_TRY(b200b_layernorm_fwd_rows(x_in, w->ln_c_g, w->ln_c_b, s.xn1, s.mean1, s.rstd1, T, D, eps, st));
   B200B_TRY(gemm(s.xn1, 0, D, w->wq_c, 0, D, T, D, D, B200B_EPI_BF16_BIAS, s.q, D, w->bq_c, nullptr, nullptr, 0, 0.f, 0,
                  0, st));
-  if (d.flags & B200B_BRIDGE_KV_PACKED) {
+  if (d.flags & (B200B_BRIDGE_KV_PACKED | B200B_BRIDGE_KV_TC)) {
     if (p != 0.f || d.L > 64) {
       set_last_error("block_forward: a packed K/V cache needs dropout_p == 0 and len_text <= 64");
       return B200B_ERR_ARG;
     }
-    B200B_TRY(b200b_attention_decode_packed(s.q, D, kv, i, d.nb, s.o1, D, s.lse1, d.B, d.Hc, d.L, d.Nv, d.dc, st));
+    if (d.flags & B200B_BRIDGE_KV_TC)
+      B200B_TRY(b200b_attention_decode_tc(s.q, D, kv, i, d.nb, s.o1, D, s.lse1, d.B, d.Hc, d.L, d.Nv, d.dc, st));
+    else
+      B200B_TRY(b200b_attention_decode_packed(s.q, D, kv, i, d.nb, s.o1, D, s.lse1, d.B, d.Hc, d.L, d.Nv, d.dc, st));
   } else {
     B200B_TRY(attn(false, s.q, D, kblk, ldkv, kblk + D, ldkv, s.o1, D, s.lse1, nullptr, nullptr, 0, nullptr, 0, nullptr,
                    0, nullptr, 0, d.B, d.Hc, d.L, d.Nv, d.dc, p, seed, (ds_cross(i) | ind), st));

@@ -8,8 +8,9 @@ but the vision K/V can: they are computed once per image here and every decode s
 
 The cache is two plain torch tensors owned by this object: `kv` (bf16, [B*Nv, num_blocks*2*D]; block
 i's K at columns [2iD, 2iD+D), V in the next D columns -- the projection output, used for steps of more
-than 64 positions) and `kv_packed` (the same values as [B][num_blocks][heads][2][Nv][d+8], the layout
-the decode kernel streams with one bulk copy per 16-key tile). The CUDA library only ever sees their
+than 64 positions), `kv_packed` (the same values as [B][num_blocks][heads][2][Nv][d+8], the layout
+the mma.sync decode kernel streams with one bulk copy per 16-key tile; steps of up to 32 positions) and
+`kv_tc` (32-key tiles as the swizzled operand images of the tcgen05 decode kernel; steps of 33..64). The CUDA library only ever sees their
 pointers for the duration of a call.
 """
 from __future__ import annotations
@@ -29,6 +30,10 @@ class VisionKVCache:
             # decode layout (per image / block / head: padded K rows then V rows), read by the K/V-streaming
             # cross-attention kernel whenever a step has <= 64 text positions
             self.kv_packed = bridge.pack_vision_kv(self.kv, self.batch, self.len_vision)
+            # tcgen05 decode layout, read by steps of 33..64 positions (where the mma.sync kernel is bound by the
+            # legacy tensor pipe); only built for the head dims that kernel is instantiated for
+            d = bridge.language_dim // bridge.num_heads_cross
+            self.kv_tc = bridge.pack_vision_kv_tc(self.kv, self.batch, self.len_vision) if d in (64, 128, 288) else None
         self._versions = tuple(p._version for p in bridge.parameters())
         self._bridge = bridge
 

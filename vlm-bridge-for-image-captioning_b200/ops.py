@@ -252,3 +252,28 @@ def attention_decode_packed(q: torch.Tensor, kv_packed: torch.Tensor, *, block_i
         q.data_ptr(), q.stride(0), kv_packed.data_ptr(), block_index, num_blocks, out.data_ptr(), out.stride(0),
         _ptr(lse), batch, heads, len_q, len_k, head_dim, _stream_ptr()), "attention_decode_packed")
     return out, lse
+
+
+def kv_cache_pack_tc(kv: torch.Tensor, *, batch: int, len_k: int, heads: int, head_dim: int,
+                     num_blocks: int) -> torch.Tensor:
+    """kv bf16 [batch*len_k, num_blocks*2*heads*head_dim] -> tcgen05 decode layout (flat uint8 tensor)."""
+    _need_cuda(kv)
+    nbytes = _lib.lib().b200b_kv_cache_tc_bytes(batch, len_k, heads, head_dim, num_blocks)
+    packed = torch.empty(nbytes, device=kv.device, dtype=torch.uint8)
+    _lib.check(_lib.lib().b200b_kv_cache_pack_tc(kv.data_ptr(), kv.stride(0), packed.data_ptr(), batch, len_k, heads,
+                                                 head_dim, num_blocks, _stream_ptr()), "kv_cache_pack_tc")
+    return packed
+
+
+def attention_decode_tc(q: torch.Tensor, kv_tc: torch.Tensor, *, block_index: int, num_blocks: int, batch: int,
+                        heads: int, len_q: int, len_k: int, head_dim: int, out: torch.Tensor | None = None,
+                        want_lse: bool = True):
+    """Cross-attention of <= 64 query rows per image against block `block_index` of a tc-packed K/V cache."""
+    _need_cuda(q, kv_tc, out)
+    if out is None:
+        out = torch.empty((batch * len_q, heads * head_dim), device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty((batch, heads, len_q), device=q.device, dtype=torch.float32) if want_lse else None
+    _lib.check(_lib.lib().b200b_attention_decode_tc(
+        q.data_ptr(), q.stride(0), kv_tc.data_ptr(), block_index, num_blocks, out.data_ptr(), out.stride(0),
+        _ptr(lse), batch, heads, len_q, len_k, head_dim, _stream_ptr()), "attention_decode_tc")
+    return out, lse
