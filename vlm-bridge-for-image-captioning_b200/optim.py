@@ -51,6 +51,7 @@ class BridgeAdamW(torch.optim.Optimizer):
         self.max_grad_norm = max_grad_norm
         self.last_grad_norm: Optional[torch.Tensor] = None
         self._steps = 0
+        self.gather_steps = 0
         self._m = self._v = self._ws = self._norm2 = self._gflat = None
 
     # -- flat state ----------------------------------------------------------------------------------
@@ -112,6 +113,7 @@ class BridgeAdamW(torch.optim.Optimizer):
                 p.grad is not None and p.grad.dtype == torch.float32 and p.grad.data_ptr() == base + 4 * lay.offsets[n]
                 for n, p in named):
             return arena
+        self.gather_steps += 1          # diagnostics: steps that could not use the arena in place
         if self._gflat is None or self._gflat.device != g0.device:
             self._gflat = torch.empty(lay.total, device=g0.device, dtype=torch.float32)
         for n, p in named:
