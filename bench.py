@@ -47,11 +47,13 @@ def total_flops_per_step(B: int, L: int, Nv: int) -> float:
     return gemm_flops_per_step(B, L, Nv) + 3.0 * attn_fwd
 
 
-def decode_bytes_per_step(B: int, s: int, Nv: int) -> float:
+def decode_bytes_per_step(B: int, s: int, Nv: int, position_rows: bool = False) -> float:
     """Algorithmic HBM bytes of the decode cross-attention at prefix length s (bf16 cache):
-    K and V of every block read once, Q read and O written."""
+    K and V of every block read once, Q read and O written. With position rows
+    block 0's launch has one query position (the new token) instead of s."""
     D = D_LANG
-    return N_BLOCKS * (B * 2.0 * Nv * D * 2 + 2.0 * B * s * D * 2)
+    lens = [1 if (position_rows and i == 0) else s for i in range(N_BLOCKS)]
+    return sum(B * 2.0 * Nv * D * 2 + 2.0 * B * lq * D * 2 for lq in lens)
 
 
 def load_peaks() -> dict:
@@ -521,6 +523,12 @@ def run_b200_arm(args) -> int:
                 line["train_step"] = bench_train_step(model, step, vision_d, text_d, args.steps)
             except Exception as e:  # noqa: BLE001
                 line["train_step"] = {"error": repr(e)[:300]}
+        # ---- fused cross-entropy over the LM logits, N=1 only ------------------
+        if world == 1 and not args.no_train_step:
+            try:
+                line["fused_ce"] = bench_fused_ce(dev, peaks)
+            except Exception as e:  # noqa: BLE001
+                line["fused_ce"] = {"error": repr(e)[:300]}
         # ---- CPU baseline beside it (N=1 only) ---------------------------------------------------
         if world == 1 and not args.no_cpu_baseline:
             v, ms, cores, sample = cpu_bridge_samples_per_s(steps=3, warmup=1, budget_s=25.0)
@@ -580,6 +588,54 @@ def bench_train_step(model, step, vision_d, text_d, steps: int) -> dict:
             "steps_that_gathered_grads": opt.gather_steps}
 
 
+def bench_fused_ce(dev, peaks) -> dict:
+    """Loss of the C2 training step: [B*L, V] = [1024, 256000] fp32 logits (what autocast hands
+    cross_entropy), labels shifted in-kernel; fwd + bwd timed with CUDA events, HBM roofline on the
+    algorithmic bytes (logits read twice, gradient written once). torch's own loss timed beside it."""
+    import torch
+    import torch.nn.functional as F
+
+    from vlm_bridge_b200 import FusedCrossEntropyLoss
+
+    rows, L, V = B_PER_GPU * L_TEXT, L_TEXT, 256000
+    g = torch.Generator().manual_seed(99)
+    logits = torch.randn(rows, V, generator=g).to(dev).requires_grad_()
+    ids = torch.randint(3, V, (B_PER_GPU, L), generator=g).to(dev)
+    labels = ids.clone()
+    labels[:, :-1] = ids[:, 1:]
+    labels[:, -1] = -100
+    loss_fn = FusedCrossEntropyLoss()
+
+    def ours():
+        logits.grad = None
+        loss_fn.forward_shifted(logits, ids).backward()
+
+    def theirs():
+        logits.grad = None
+        F.cross_entropy(logits, labels.view(-1), ignore_index=-100).backward()
+
+    out = {}
+    for name, fn in (("fused", ours), ("torch", theirs)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = e0.elapsed_time(e1) / reps
+    nbytes = 3.0 * rows * V * 4
+    achieved = nbytes / (out["fused"] * 1e-3) / 1e9
+    return {"metric": "cross-entropy fwd+bwd over [1024, 256000] fp32 logits", "ms": out["fused"], "torch_ms": out["torch"],
+            "roofline": {"bound": "hbm", "kernel": "ce_fwd_kernel + ce_bwd_kernel", "achieved": achieved,
+                         "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"],
+                         "algorithmic_bytes": nbytes, "traffic": None},
+            "note": "inputs (2.1 GB with the gradient) exceed the 126 MB L2; includes the autograd node overhead"}
+
+
 def bench_decode(model, dev, peaks, _lib) -> dict:
     """Config C4: greedy-decode-shaped loop, batch 32, 64 steps, prefix length s = 1..64, bridge only
     (the frozen LM is outside the hot path). The per-image K/V are projected once and cached."""
@@ -592,13 +648,15 @@ def bench_decode(model, dev, peaks, _lib) -> dict:
     vision = torch.randn(DEC_B, N_VIS, D_VIS, generator=g).to(dev)
     text = torch.randn(DEC_B, DEC_STEPS, D_LANG, generator=g).to(dev)
 
-    def loop(cache, graphs=None):
+    def loop(cache, graphs=None, rows=True):
+        # rows: block 0's cross-attention rows are kept per text position (computed for the new token only)
         with torch.no_grad():
             for s in range(1, DEC_STEPS + 1):
+                k = s - 1 if (rows and cache is not None) else None
                 if graphs is not None:
-                    graphs(text[:, :s])
+                    graphs(text[:, :s], cached_positions=k)
                 else:
-                    model(vision, text[:, :s], kv_cache=cache)
+                    model(vision, text[:, :s], kv_cache=cache, cached_positions=k)
 
     with torch.no_grad():
         cache = VisionKVCache(model, vision)
@@ -637,13 +695,22 @@ def bench_decode(model, dev, peaks, _lib) -> dict:
     except Exception as e:  # noqa: BLE001
         graph_err = repr(e)[:200]
     ms = min(ms_eager, ms_graph) if ms_graph is not None else ms_eager
+    # K/V cache only (every text row of block 0's cross-attention recomputed every step), eager
+    loop(cache, rows=False)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        loop(cache, rows=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_kv_only = e0.elapsed_time(e1) / reps
     # kernel-level: cross-attention launches only
     _lib.profile_begin(torch.cuda.current_stream().cuda_stream)
     loop(cache)
     entries = _lib.profile_end()
     # cross-attention launches over the cached K/V: the packed-layout decode kernel
     cross_ms = sum(ms_ for name, ms_ in entries if name in ("attn_decode_packed", "attn_decode_tc"))
-    bytes_total = sum(decode_bytes_per_step(DEC_B, s, N_VIS) for s in range(1, DEC_STEPS + 1))
+    bytes_total = sum(decode_bytes_per_step(DEC_B, s, N_VIS, position_rows=True) for s in range(1, DEC_STEPS + 1))
     achieved = bytes_total / (cross_ms * 1e-3) / 1e9 if cross_ms > 0 else 0.0
     return {
         "metric": "caption decode tokens/sec (bridge-only loop, cached vision K/V)",
@@ -651,8 +718,11 @@ def bench_decode(model, dev, peaks, _lib) -> dict:
         "ms_per_caption_batch_by_launch_mode": {"eager (incl. K/V projection + packing per caption batch)": ms_eager,
                                                 "graph replay per prefix length (cache and graphs reused)": ms_graph},
         "uncached_tokens_per_s": DEC_B * DEC_STEPS / (ms_uncached * 1e-3),
-        "config": f"C4: batch {DEC_B}, {DEC_STEPS} new tokens, prefix recomputed every step (non-causal bridge), Nv={N_VIS}",
-        "roofline": {"bound": "hbm", "kernel": "attn_decode_kernel<288, packed> for <= 32 positions, attn_decode_tc_kernel<288> above (the 128 cross-attention launches)", "achieved": achieved,
+        "kv_cache_only_tokens_per_s": DEC_B * DEC_STEPS / (ms_kv_only * 1e-3),
+        "config": (f"C4: batch {DEC_B}, {DEC_STEPS} new tokens, Nv={N_VIS}; vision K/V cached per image, block 0's "
+                   "cross-attention rows cached per text position, everything from block 0's non-causal "
+                   "self-attention on recomputed over the prefix every step"),
+        "roofline": {"bound": "hbm", "kernel": "attn_decode_kernel<288, packed> for <= 32 positions (all 64 block-0 launches: 1 position each), attn_decode_tc_kernel<288> above (the 128 cross-attention launches)", "achieved": achieved,
                      "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": None,
                      "algorithmic_bytes_total": bytes_total, "kernel_ms_total": cross_ms,
                      "note": ("event-timed between eager launches. Graph-timed per launch (profiles/r01_exp_decode_v3.jsonl, "

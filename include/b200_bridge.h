@@ -257,6 +257,14 @@ typedef struct b200b_bridge_dims {
 /* flags (block_forward only): `kv` is the tcgen05 decode cache written by b200b_kv_cache_pack_tc; the
  * cross-attention runs b200b_attention_decode_tc. Same conditions as B200B_BRIDGE_KV_PACKED. */
 #define B200B_BRIDGE_KV_TC 8
+/* flags (block_forward only, inference: dropout_p == 0): run one part of the block.
+ * PART_CROSS: only the cross-attention sub-layer (bridge_module.py:316-323); x_out receives
+ *             x1 = x_in + W_o * SDPA(W_q * LN(x_in), K, V). A row of x1 depends on the same row of x_in
+ *             and on the image only, so decode computes it once per text position.
+ * PART_REST:  skip that sub-layer; x_in is x1 and the self-attention and FFN sub-layers (:326-333) run.
+ * Neither bit: the whole block. Both bits: B200B_ERR_ARG. */
+#define B200B_BRIDGE_PART_CROSS 16
+#define B200B_BRIDGE_PART_REST 32
 /* The same for the individual operators: OR this bit into `dropout_stream` and pass the device
  * pointer (cast to uint64_t) as `seed`. */
 #define B200B_SEED_INDIRECT 0x80000000u
@@ -358,6 +366,33 @@ int b200b_adamw_fused(float* param, const float* grad, float* exp_avg, float* ex
                       int64_t n, int64_t n_bf16, const float* sqnorm2, float max_grad_norm,
                       const float* grad_scale, const float* found_inf, float lr, float beta1, float beta2,
                       float eps, float weight_decay, int64_t step, void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
+ * Fused cross-entropy over the vocabulary logits. Replaces the label shift and
+ * nn.CrossEntropyLoss(ignore_index=-100)(logits.view(-1, V), labels.view(-1)) of the reference training
+ * step (core_training_loop.py:51-55,68-69) and its autograd backward.
+ *
+ * logits [rows, vocab], row pitch ld elements, dtype 0 = f32, 1 = bf16 (arithmetic is fp32 either way,
+ * as autocast runs cross_entropy in fp32). labels int64 [rows]; or, with shift_len = L > 0, the
+ * [rows / L, L] input_ids, from which row r takes input_ids[r + 1] and the last position of every
+ * sequence is ignored (:52-54). Rows whose label equals ignore_index contribute nothing; a label
+ * outside [0, vocab) makes the loss NaN (PyTorch device-asserts instead).
+ *
+ * fwd: lse f32 [rows] = log sum exp of each row (kept for bwd), loss_rows f32 [rows] = per-row loss,
+ *      out2[0] = mean loss over the non-ignored rows (NaN if there are none), out2[1] = their count.
+ * bwd: dlogits [rows, vocab] (row pitch ldd, same dtype as logits)
+ *        = (softmax(logits) - onehot(label)) * *grad_loss / out2[1], 0 for ignored rows;
+ *      grad_loss is a device scalar (the upstream gradient of the mean loss, e.g. the GradScaler scale).
+ * Two launches forward (row pass + finalize), one backward; nothing but lse / out2 is saved. 16-byte
+ * vector accesses when vocab % 8 == 0 and rows are 16-byte aligned, scalar otherwise.
+ * ------------------------------------------------------------------------------------------- */
+int b200b_cross_entropy_fwd(const void* logits, int dtype, int64_t ld, const int64_t* labels, int64_t rows,
+                            int64_t vocab, int64_t ignore_index, int64_t shift_len, float* lse,
+                            float* loss_rows, float* out2, void* stream);
+int b200b_cross_entropy_bwd(const void* logits, int dtype, int64_t ld, const int64_t* labels, int64_t rows,
+                            int64_t vocab, int64_t ignore_index, int64_t shift_len, const float* lse,
+                            const float* out2, const float* grad_loss, void* dlogits, int64_t ldd,
+                            void* stream);
 
 /* out f32 [n] = scale * in bf16 [n] (n % 8 == 0): turns an exchanged bf16 gradient bucket into
  * the fp32 .grad the optimizer reads. */

@@ -65,11 +65,14 @@ def test_greedy_decode_matches_oracle_and_is_sync_free_batched():
     head = torch.randn(V, 2304, generator=g) / 48.0
     m = _model(sd)
     embed_d, head_d = embed.cuda(), head.cuda()
-    ids, lengths = greedy_decode(m, vision.cuda(), lambda t: embed_d[t], lambda h: h[:, -1, :] @ head_d.t(),
-                                 bos_token_id=2, eos_token_id=1, max_new_tokens=steps)
+    ids_kv, _ = greedy_decode(m, vision.cuda(), lambda t: embed_d[t], lambda h: h[:, -1, :] @ head_d.t(),
+                              bos_token_id=2, eos_token_id=1, max_new_tokens=steps, cache_positions=False)
     ids_nc, _ = greedy_decode(m, vision.cuda(), lambda t: embed_d[t], lambda h: h[:, -1, :] @ head_d.t(),
                               bos_token_id=2, eos_token_id=1, max_new_tokens=steps, use_cache=False)
-    assert torch.equal(ids, ids_nc)                      # cache on / off: identical token ids
+    assert torch.equal(ids_kv, ids_nc)                   # K/V cache on / off: identical token ids
+    # default: K/V cache + per-position rows of block 0's cross-attention (checked against the oracle below)
+    ids, lengths = greedy_decode(m, vision.cuda(), lambda t: embed_d[t], lambda h: h[:, -1, :] @ head_d.t(),
+                                 bos_token_id=2, eos_token_id=1, max_new_tokens=steps)
     ids_g, _ = greedy_decode(m, vision.cuda(), lambda t: embed_d[t], lambda h: h[:, -1, :] @ head_d.t(),
                              bos_token_id=2, eos_token_id=1, max_new_tokens=steps, use_graphs=True)
     assert torch.equal(ids, ids_g)                       # one graph replay per prefix length: identical
@@ -92,6 +95,55 @@ def test_greedy_decode_matches_oracle_and_is_sync_free_batched():
         row = ids_c[b, 1:].tolist()
         want = (row.index(1) + 1) if 1 in row else steps + 1
         assert int(lengths[b]) == want
+
+
+@pytest.mark.parametrize("s", [1, 6, 33, 64])
+def test_position_rows_match_full_recompute(s):
+    """Block 0's cross-attention rows kept per text position: a prefix grown one
+    token at a time with `cached_positions` gives the K/V-cached full recompute within 5e-3 of the output
+    maximum (the new row goes through the 1-position decode kernel instead of the s-position one: same
+    bf16 operands, different fp32 summation order) and the fp32 oracle within 2e-2."""
+    from vlm_bridge_b200 import VisionKVCache
+
+    sd = O.init_state_dict(0)
+    g = torch.Generator().manual_seed(300 + s)
+    B, Nv = 2, 257
+    vision = torch.randn(B, Nv, 1024, generator=g)
+    text = torch.randn(B, s, 2304, generator=g)
+    m = _model(sd)
+    tc = text.cuda()
+    with torch.no_grad():
+        cache = VisionKVCache(m, vision.cuda())
+        y_full = m(None, tc, kv_cache=cache)
+        for j in range(1, s + 1):
+            y_inc = m(None, tc[:, :j], kv_cache=cache, cached_positions=j - 1)
+        assert float((y_inc - y_full).abs().max() / y_full.abs().max()) <= 5e-3
+        if s >= 6:
+            # several new positions at once, after refilling from scratch
+            m(None, tc[:, :2], kv_cache=cache, cached_positions=0)
+            y_multi = m(None, tc, kv_cache=cache, cached_positions=2)
+            assert float((y_multi - y_full).abs().max() / y_full.abs().max()) <= 5e-3
+    y_ref = O.bridge_forward_cached(sd, O.vision_kv(sd, vision), text)
+    assert float((y_inc.cpu() - y_ref).abs().max() / y_ref.abs().max()) <= 2e-2
+
+
+def test_position_rows_guards():
+    from vlm_bridge_b200 import VisionKVCache
+
+    m = _model(O.init_state_dict(2))
+    vision = torch.randn(1, 17, 1024).cuda()
+    text = torch.randn(1, 70, 2304).cuda()
+    with torch.no_grad():
+        cache = VisionKVCache(m, vision, max_positions=8)
+        with pytest.raises(RuntimeError):                 # rows that were never written
+            m(None, text[:, :4], kv_cache=cache, cached_positions=3)
+        m(None, text[:, :4], kv_cache=cache, cached_positions=0)
+        with pytest.raises(RuntimeError):                 # k must leave at least one new position
+            m(None, text[:, :4], kv_cache=cache, cached_positions=4)
+        # a prefix longer than the row store: every row is computed, i.e. the plain K/V-cached path
+        assert torch.equal(m(None, text[:, :9], kv_cache=cache, cached_positions=4), m(None, text[:, :9], kv_cache=cache))
+    with pytest.raises(RuntimeError):                     # inference only
+        m(vision, text[:, :4].requires_grad_(), cached_positions=0)
 
 
 def test_stale_cache_is_detected():

@@ -99,3 +99,57 @@ def test_nonfinite_gradients_skip_the_step():
     next(m.parameters()).grad[0, 0] = float("inf")
     opt.step()
     assert torch.equal(m._flat, before)
+
+
+def test_loss_trajectory_100_steps_matches_reference_numerics():
+    """BASELINE.json north_star: "loss within 1e-3 over 100 steps". The CUDA training loop (bridge fwd+bwd
+    kernels + fused clip/AdamW) against the CPU oracle training with torch.optim.AdamW +
+    clip_grad_norm_ (core_training_loop.py:84-104; clip 0.3 = config/training-default.yaml:9) on the same
+    batches from the same initial weights, 100 steps. Compared with the oracle in the reference's
+    training numerics (bf16-rounded GEMM operands, as torch.autocast gives) at
+    |d loss| <= 1e-3 * max(1, loss) per step, and with the pure-fp32 oracle at twice that (the fp32 and
+    bf16-emulating oracles themselves differ by up to 5e-4 on this run)."""
+    from oracle import bridge_oracle as O
+    from vlm_bridge_b200 import BridgeAdamW, BridgeLite
+
+    cfg = dict(vision_dim=64, language_dim=128, num_blocks=2, num_heads_cross=2, num_heads_self=1)
+    steps, lr, wd, clip = 100, 1e-4, 0.01, 0.3
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.randn(4, 17, 64, generator=g), torch.randn(4, 12, 128, generator=g)) for _ in range(4)]
+    sd0 = O.init_state_dict(0, vision_dim=64, language_dim=128, num_blocks=2)
+
+    def oracle_run(emulate_bf16):
+        params = {k: v.clone().requires_grad_() for k, v in sd0.items()}
+        opt = torch.optim.AdamW(list(params.values()), lr=lr, weight_decay=wd)
+        out = []
+        for s in range(steps):
+            v, t = batches[s % 4]
+            opt.zero_grad()
+            loss = O.bridge_forward(params, v, t, num_blocks=2, heads_cross=2, heads_self=1,
+                                    emulate_bf16=emulate_bf16).square().mean()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(list(params.values()), clip)
+            opt.step()
+            out.append(float(loss.detach()))
+        return torch.tensor(out)
+
+    m = BridgeLite(dropout=0.0, **cfg)
+    m.load_state_dict(sd0, strict=True)
+    m = m.cuda().train()
+    opt = BridgeAdamW(m, lr=lr, weight_decay=wd, max_grad_norm=clip)
+    dev_batches = [(v.cuda(), t.cuda()) for v, t in batches]
+    losses = []
+    for s in range(steps):
+        v, t = dev_batches[s % 4]
+        opt.zero_grad(set_to_none=True)
+        loss = m(v, t).float().square().mean()
+        loss.backward()
+        opt.step()
+        losses.append(loss.detach())
+    got = torch.stack(losses).cpu()
+    ref16, ref32 = oracle_run(True), oracle_run(False)
+    assert float(ref32[-1]) < 0.5 * float(ref32[0])        # the run really trains
+    dev16 = ((got - ref16).abs() / ref16.clamp_min(1.0)).max()
+    dev32 = ((got - ref32).abs() / ref32.clamp_min(1.0)).max()
+    assert float(dev16) <= 1e-3, (float(dev16), float(dev32))
+    assert float(dev32) <= 2e-3, (float(dev16), float(dev32))

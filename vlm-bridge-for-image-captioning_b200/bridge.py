@@ -183,6 +183,8 @@ FLAG_WGRAD_BF16 = 1      # B200B_BRIDGE_WGRAD_BF16
 FLAG_SEED_INDIRECT = 2   # B200B_BRIDGE_SEED_INDIRECT
 FLAG_KV_PACKED = 4       # B200B_BRIDGE_KV_PACKED
 FLAG_KV_TC = 8           # B200B_BRIDGE_KV_TC
+FLAG_PART_CROSS = 16     # B200B_BRIDGE_PART_CROSS
+FLAG_PART_REST = 32      # B200B_BRIDGE_PART_REST
 TC_DECODE_MIN_LEN = 33   # prefix lengths from which the tcgen05 decode kernel beats the mma.sync one (measured)
 _SEED_STRIDE = 0x1E3779B97F4A7C15  # odd 61-bit increment of the device-resident dropout seed
 _GRAD_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int64)
@@ -443,8 +445,19 @@ class BridgeLite(nn.Module):
         return packed
 
     # -- forward / backward drivers ----------------------------------------------------------------
+    def _kv_flag(self, kv_cache, L: int, keep_for_backward: bool):
+        """(kv tensor, B200B_BRIDGE_KV_* flag) a cross-attention over L text positions reads from `kv_cache`."""
+        packed = (kv_cache is not None and not keep_for_backward and L <= 64 and not (self.training and self.dropout_p > 0)
+                  and getattr(kv_cache, "kv_packed", None) is not None
+                  and (self.language_dim // self.num_heads_cross) in (64, 128, 288))
+        if not packed:
+            return kv_cache.kv, 0
+        if L >= TC_DECODE_MIN_LEN and getattr(kv_cache, "kv_tc", None) is not None:
+            return kv_cache.kv_tc, FLAG_KV_TC
+        return kv_cache.kv_packed, FLAG_KV_PACKED
+
     def _run_forward(self, vision: torch.Tensor, text: torch.Tensor, keep_for_backward: bool, kv_cache=None,
-                     block_callback=None):
+                     block_callback=None, cached_positions: Optional[int] = None):
         self._ensure_flat()
         self._refresh_bf16()
         dev = self._flat.device
@@ -465,12 +478,9 @@ class BridgeLite(nn.Module):
                 raise RuntimeError("kv cache batch does not match text batch")
         lib = _bridge_lib()
         dims = self._dims(B, L, Nv)
-        packed = (kv_cache is not None and not keep_for_backward and L <= 64 and not (self.training and self.dropout_p > 0)
-                  and getattr(kv_cache, "kv_packed", None) is not None
-                  and (self.language_dim // self.num_heads_cross) in (64, 128, 288))
-        use_tc = packed and L >= TC_DECODE_MIN_LEN and getattr(kv_cache, "kv_tc", None) is not None
-        if packed:
-            kv = kv_cache.kv_tc if use_tc else kv_cache.kv_packed
+        kv_flag = 0
+        if kv_cache is not None:
+            kv, kv_flag = self._kv_flag(kv_cache, L, keep_for_backward)
         saved_bytes = lib.b200b_bridge_block_saved_bytes(C.byref(dims))
         n_arenas = self.num_blocks if keep_for_backward else 1
         saved = torch.empty(n_arenas * saved_bytes, device=dev, dtype=torch.uint8)
@@ -482,18 +492,38 @@ class BridgeLite(nn.Module):
                 # with a captured kernel, and let every dropout kernel read it when it runs
                 self._seed_dev.add_(_SEED_STRIDE)
                 seed, flags = self._seed_dev.data_ptr(), FLAG_SEED_INDIRECT
-                dims = self._dims(B, L, Nv, flags)
             else:
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-        if packed:
-            dims = self._dims(B, L, Nv, flags | (FLAG_KV_TC if use_tc else FLAG_KV_PACKED))
+        dims = self._dims(B, L, Nv, flags | kv_flag)
         ptrs = self._weight_ptrs()
         xs = [x.view(B * L, D)]
         st = _stream()
+        # decode: block 0's cross-attention sub-layer is row-wise in the text (a row of its output depends
+        # on the same text row and on the image only), so its rows are kept per position in the cache and
+        # only the rows from `cached_positions` on are computed
+        pos_cache = None
+        if cached_positions is not None:
+            if kv_cache is None or keep_for_backward or p > 0:
+                raise RuntimeError("cached_positions needs kv_cache, inference mode and no active dropout")
+            pos_cache = kv_cache.position_rows(L, cached_positions, dev, D)
         for i in range(self.num_blocks):
             x_out = torch.empty((B * L, D), device=dev, dtype=torch.float32)
             arena = saved.data_ptr() + (i if keep_for_backward else 0) * saved_bytes
-            _lib.check(lib.b200b_bridge_block_forward(C.byref(dims), i, C.byref(ptrs[i]), xs[-1].data_ptr(),
+            x_in, bdims = xs[-1], dims
+            if i == 0 and pos_cache is not None:
+                k = int(cached_positions)
+                n_new = L - k
+                x_new = x[:, k:, :].contiguous()
+                kv_c, flag_c = self._kv_flag(kv_cache, n_new, False)
+                cdims = self._dims(B, n_new, Nv, flag_c | FLAG_PART_CROSS)
+                x1_new = torch.empty((B * n_new, D), device=dev, dtype=torch.float32)
+                _lib.check(lib.b200b_bridge_block_forward(C.byref(cdims), 0, C.byref(ptrs[0]), x_new.data_ptr(),
+                                                          kv_c.data_ptr(), x1_new.data_ptr(), arena, saved_bytes, 0.0, 0,
+                                                          st), "block_forward(cross part)")
+                pos_cache[:, k:L].copy_(x1_new.view(B, n_new, D))
+                x_in = pos_cache[:, :L].contiguous().view(B * L, D)
+                bdims = self._dims(B, L, Nv, FLAG_PART_REST)
+            _lib.check(lib.b200b_bridge_block_forward(C.byref(bdims), i, C.byref(ptrs[i]), x_in.data_ptr(),
                                                       kv.data_ptr(), x_out.data_ptr(), arena, saved_bytes, p, seed,
                                                       st), "block_forward")
             if block_callback is not None:
@@ -600,22 +630,27 @@ class BridgeLite(nn.Module):
 
     # -- public API ----------------------------------------------------------------------------------
     def forward(self, vision_features: torch.Tensor, text_embeddings: torch.Tensor, debug: bool = False,
-                kv_cache=None) -> torch.Tensor:
+                kv_cache=None, cached_positions: Optional[int] = None) -> torch.Tensor:
         """Same contract as the reference `BridgeLite.forward` (bridge_module.py:406-456).
 
         `kv_cache` (a `VisionKVCache`) is an additive, inference-only argument: when given, the
         per-image K/V projections are read from the cache instead of being recomputed.
+        `cached_positions=k` (with `kv_cache`, eval mode) additionally declares that the first k text
+        positions are the ones this cache last saw at those positions (a decode loop appending
+        tokens): block 0's cross-attention rows of those positions are reused from the cache and
+        only positions k.. are computed; k=0 (re)fills the cache from scratch.
         """
         params = [p for _, p in self._named_params()]
         needs_grad = torch.is_grad_enabled() and (text_embeddings.requires_grad or any(p.requires_grad for p in params))
         if debug:
             return self._forward_debug(vision_features, text_embeddings, kv_cache)
         if needs_grad:
-            if kv_cache is not None:
+            if kv_cache is not None or cached_positions is not None:
                 raise RuntimeError("kv_cache is inference-only (use torch.no_grad())")
             out = _BridgeFunction.apply(self, vision_features, text_embeddings, *params)
         else:
-            out, _ = self._run_forward(vision_features, text_embeddings, keep_for_backward=False, kv_cache=kv_cache)
+            out, _ = self._run_forward(vision_features, text_embeddings, keep_for_backward=False, kv_cache=kv_cache,
+                                       cached_positions=cached_positions)
         return out if text_embeddings.dtype == torch.float32 else out
 
     def _forward_debug(self, vision_features, text_embeddings, kv_cache):

@@ -232,32 +232,49 @@ extern "C" int b200b_bridge_block_forward(const b200b_bridge_dims* dims, int i, 
   const __nv_bfloat16* kblk = reinterpret_cast<const __nv_bfloat16*>(kv) + (size_t)2 * D * i;
   const float eps = 1e-5f;
 
-  // 1. cross-attention: x1 = x + W_o * SDPA(W_q * LN(x), K_i, V_i)          (bridge_module.py:316-323)
-  B200B_TRY(b200b_layernorm_fwd_rows(x_in, w->ln_c_g, w->ln_c_b, s.xn1, s.mean1, s.rstd1, T, D, eps, st));
-  B200B_TRY(gemm(s.xn1, 0, D, w->wq_c, 0, D, T, D, D, B200B_EPI_BF16_BIAS, s.q, D, w->bq_c, nullptr, nullptr, 0, 0.f, 0,
-                 0, st));
-  if (d.flags & (B200B_BRIDGE_KV_PACKED | B200B_BRIDGE_KV_TC)) {
-    if (p != 0.f || d.L > 64) {
-      set_last_error("block_forward: a packed K/V cache needs dropout_p == 0 and len_text <= 64");
-      return B200B_ERR_ARG;
-    }
-    if (d.flags & B200B_BRIDGE_KV_TC)
-      B200B_TRY(b200b_attention_decode_tc(s.q, D, kv, i, d.nb, s.o1, D, s.lse1, d.B, d.Hc, d.L, d.Nv, d.dc, st));
-    else
-      B200B_TRY(b200b_attention_decode_packed(s.q, D, kv, i, d.nb, s.o1, D, s.lse1, d.B, d.Hc, d.L, d.Nv, d.dc, st));
-  } else {
-    B200B_TRY(attn(false, s.q, D, kblk, ldkv, kblk + D, ldkv, s.o1, D, s.lse1, nullptr, nullptr, 0, nullptr, 0, nullptr,
-                   0, nullptr, 0, d.B, d.Hc, d.L, d.Nv, d.dc, p, seed, (ds_cross(i) | ind), st));
+  // B200B_BRIDGE_PART_*: decode runs the position-independent cross-attention sub-layer once per text
+  // position and the rest of the block on the whole prefix
+  const bool do_cross = !(d.flags & B200B_BRIDGE_PART_REST), do_rest = !(d.flags & B200B_BRIDGE_PART_CROSS);
+  if (!do_cross && !do_rest) {
+    set_last_error("block_forward: PART_CROSS and PART_REST are exclusive");
+    return B200B_ERR_ARG;
   }
-  B200B_TRY(gemm(s.o1, 0, D, w->wo_c, 0, D, T, D, D, B200B_EPI_F32_BIAS_RESID, s.x1, D, w->bo_c, x_in, nullptr, 0, 0.f,
-                 0, 0, st));
+  if ((!do_cross || !do_rest) && p != 0.f) {
+    set_last_error("block_forward: running a part of a block needs dropout_p == 0");
+    return B200B_ERR_ARG;
+  }
+  float* x1w = do_rest ? s.x1 : x_out;                 // where the cross sub-layer writes
+  const float* x1 = do_cross ? x1w : x_in;             // what the rest of the block reads
+
+  // 1. cross-attention: x1 = x + W_o * SDPA(W_q * LN(x), K_i, V_i)          (bridge_module.py:316-323)
+  if (do_cross) {
+    B200B_TRY(b200b_layernorm_fwd_rows(x_in, w->ln_c_g, w->ln_c_b, s.xn1, s.mean1, s.rstd1, T, D, eps, st));
+    B200B_TRY(gemm(s.xn1, 0, D, w->wq_c, 0, D, T, D, D, B200B_EPI_BF16_BIAS, s.q, D, w->bq_c, nullptr, nullptr, 0, 0.f,
+                   0, 0, st));
+    if (d.flags & (B200B_BRIDGE_KV_PACKED | B200B_BRIDGE_KV_TC)) {
+      if (p != 0.f || d.L > 64) {
+        set_last_error("block_forward: a packed K/V cache needs dropout_p == 0 and len_text <= 64");
+        return B200B_ERR_ARG;
+      }
+      if (d.flags & B200B_BRIDGE_KV_TC)
+        B200B_TRY(b200b_attention_decode_tc(s.q, D, kv, i, d.nb, s.o1, D, s.lse1, d.B, d.Hc, d.L, d.Nv, d.dc, st));
+      else
+        B200B_TRY(b200b_attention_decode_packed(s.q, D, kv, i, d.nb, s.o1, D, s.lse1, d.B, d.Hc, d.L, d.Nv, d.dc, st));
+    } else {
+      B200B_TRY(attn(false, s.q, D, kblk, ldkv, kblk + D, ldkv, s.o1, D, s.lse1, nullptr, nullptr, 0, nullptr, 0,
+                     nullptr, 0, nullptr, 0, d.B, d.Hc, d.L, d.Nv, d.dc, p, seed, (ds_cross(i) | ind), st));
+    }
+    B200B_TRY(gemm(s.o1, 0, D, w->wo_c, 0, D, T, D, D, B200B_EPI_F32_BIAS_RESID, x1w, D, w->bo_c, x_in, nullptr, 0, 0.f,
+                   0, 0, st));
+  }
+  if (!do_rest) return B200B_OK;
   // 2. self-attention (non-causal, unmasked)                                 (:326-328)
-  B200B_TRY(b200b_layernorm_fwd_rows(s.x1, w->ln_s_g, w->ln_s_b, s.xn2, s.mean2, s.rstd2, T, D, eps, st));
+  B200B_TRY(b200b_layernorm_fwd_rows(x1, w->ln_s_g, w->ln_s_b, s.xn2, s.mean2, s.rstd2, T, D, eps, st));
   B200B_TRY(gemm(s.xn2, 0, D, w->wqkv_s, 0, D, T, 3 * D, D, B200B_EPI_BF16_BIAS, s.qkv, 3 * D, w->bqkv_s, nullptr,
                  nullptr, 0, 0.f, 0, 0, st));
   B200B_TRY(attn(false, s.qkv, 3 * D, s.qkv + D, 3 * D, s.qkv + 2 * D, 3 * D, s.o2, D, s.lse2, nullptr, nullptr, 0,
                  nullptr, 0, nullptr, 0, nullptr, 0, d.B, d.Hs, d.L, d.L, d.ds, p, seed, (ds_self(i) | ind), st));
-  B200B_TRY(gemm(s.o2, 0, D, w->wo_s, 0, D, T, D, D, B200B_EPI_F32_BIAS_RESID, s.x2, D, w->bo_s, s.x1, nullptr, 0, 0.f,
+  B200B_TRY(gemm(s.o2, 0, D, w->wo_s, 0, D, T, D, D, B200B_EPI_F32_BIAS_RESID, s.x2, D, w->bo_s, x1, nullptr, 0, 0.f,
                  0, 0, st));
   // 3. FFN: x3 = x2 + drop(W_2 * drop(gelu(W_1 * LN(x2))))                    (:331-333)
   B200B_TRY(b200b_layernorm_fwd_rows(s.x2, w->ln_f_g, w->ln_f_b, s.xn3, s.mean3, s.rstd3, T, D, eps, st));

@@ -40,18 +40,24 @@ class DecodeStepGraphs:
         self._graphs: dict = {}
         self._pool = None
 
-    def __call__(self, text_embeddings: torch.Tensor) -> torch.Tensor:
-        """bridge(vision, text_embeddings, kv_cache=cache) for text_embeddings [B, s, D]; the returned
-        tensor is the graph's static output (overwritten by the next call with the same shape)."""
+    def __call__(self, text_embeddings: torch.Tensor, cached_positions: Optional[int] = None) -> torch.Tensor:
+        """bridge(vision, text_embeddings, kv_cache=cache, cached_positions=...) for text_embeddings
+        [B, s, D]; the returned tensor is the graph's static output (overwritten by the next call with
+        the same shape)."""
         if not self.cache.is_current():
             raise RuntimeError("the K/V cache is stale (bridge weights changed): rebuild it and the graphs")
-        key = (int(text_embeddings.shape[0]), int(text_embeddings.shape[1]))
+        key = (int(text_embeddings.shape[0]), int(text_embeddings.shape[1]), cached_positions)
+        if cached_positions is not None:
+            # the host-side bookkeeping a replay skips (also validates the request)
+            if self.cache.position_rows(key[1], cached_positions, text_embeddings.device, text_embeddings.shape[-1]) is None:
+                key = key[:2] + (None,)
+                cached_positions = None
         ent = self._graphs.get(key)
         if ent is None:
             b = self.bridge
             static_in = text_embeddings.detach().to(torch.float32).clone()
             with torch.no_grad():
-                b(None, static_in, kv_cache=self.cache)           # lazy initialisation outside the capture
+                b(None, static_in, kv_cache=self.cache, cached_positions=cached_positions)   # lazy init outside the capture
                 torch.cuda.synchronize()
                 if self._pool is None:
                     self._pool = torch.cuda.graph_pool_handle()
@@ -59,7 +65,7 @@ class DecodeStepGraphs:
                 recast, b._graph_recast = b._graph_recast, False
                 try:
                     with torch.cuda.graph(g, pool=self._pool):
-                        out = b(None, static_in, kv_cache=self.cache)
+                        out = b(None, static_in, kv_cache=self.cache, cached_positions=cached_positions)
                 finally:
                     b._graph_recast = recast
             ent = self._graphs[key] = (g, static_in, out)
@@ -74,11 +80,15 @@ def greedy_decode(bridge, vision_features: torch.Tensor, embed_fn: Callable[[tor
                   lm_fn: Callable[[torch.Tensor], torch.Tensor], *, bos_token_id: int,
                   eos_token_id: Optional[int] = None, max_new_tokens: int = 50,
                   kv_cache: Optional[VisionKVCache] = None, use_cache: bool = True,
-                  step_graphs: Optional[DecodeStepGraphs] = None, use_graphs: bool = False):
+                  step_graphs: Optional[DecodeStepGraphs] = None, use_graphs: bool = False,
+                  cache_positions: bool = True):
     """Returns (ids [B, 1 + max_new_tokens] int64 incl. BOS, lengths [B] int64): row b's caption is
     ids[b, 1:lengths[b]] (EOS excluded); positions from lengths[b] on are what the lock-step loop kept
     generating and are to be ignored. `use_graphs` replays one captured CUDA graph of the bridge per
-    prefix length (`DecodeStepGraphs`; pass `step_graphs` to reuse graphs captured for the same cache)."""
+    prefix length (`DecodeStepGraphs`; pass `step_graphs` to reuse graphs captured for the same cache).
+    `cache_positions` keeps block 0's cross-attention rows per text position in the cache (valid because
+    `embed_fn` is a per-token lookup: the prefix rows do not change when a token is appended); pass
+    False for an `embed_fn` that mixes positions."""
     was_training = bridge.training
     bridge.eval()
     try:
@@ -95,10 +105,12 @@ def greedy_decode(bridge, vision_features: torch.Tensor, embed_fn: Callable[[tor
         ids[:, 0] = bos_token_id
         for step in range(max_new_tokens):
             prefix = ids[:, :step + 1]
+            kpos = step if (cache_positions and use_cache) else None
             if step_graphs is not None:
-                hidden = step_graphs(embed_fn(prefix))
+                hidden = step_graphs(embed_fn(prefix), cached_positions=kpos)
             else:
-                hidden = bridge(vision_features, embed_fn(prefix), kv_cache=kv_cache if use_cache else None)
+                hidden = bridge(vision_features, embed_fn(prefix), kv_cache=kv_cache if use_cache else None,
+                                cached_positions=kpos)
             logits = lm_fn(hidden)
             if logits.dim() == 3:
                 logits = logits[:, -1, :]

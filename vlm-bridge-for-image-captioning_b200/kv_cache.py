@@ -12,6 +12,13 @@ than 64 positions), `kv_packed` (the same values as [B][num_blocks][heads][2][Nv
 the mma.sync decode kernel streams with one bulk copy per 16-key tile; steps of up to 32 positions) and
 `kv_tc` (32-key tiles as the swizzled operand images of the tcgen05 decode kernel; steps of 33..64). The CUDA library only ever sees their
 pointers for the duration of a call.
+
+Position rows (`x1`, fp32 [B, max_positions, D]): block 0's cross-attention sub-layer
+(bridge_module.py:316-323) maps text row (b, j) to x1[b, j] = x + W_o * SDPA(W_q * LN(x), K_b, V_b),
+which involves no other text position, so a decode loop that appends tokens computes it once per
+position (`BridgeLite.forward(..., kv_cache=cache, cached_positions=k)`) instead of once per position
+per step. Everything after it (block 0's non-causal self-attention onwards) mixes positions and is
+recomputed on the whole prefix, as in the reference.
 """
 from __future__ import annotations
 
@@ -21,7 +28,7 @@ __all__ = ["VisionKVCache"]
 
 
 class VisionKVCache:
-    def __init__(self, bridge, vision_features: torch.Tensor):
+    def __init__(self, bridge, vision_features: torch.Tensor, max_positions: int = 64):
         if vision_features.dim() != 3:
             raise RuntimeError("vision_features must be [B, Nv, vision_dim]")
         self.batch, self.len_vision = int(vision_features.shape[0]), int(vision_features.shape[1])
@@ -36,6 +43,27 @@ class VisionKVCache:
             self.kv_tc = bridge.pack_vision_kv_tc(self.kv, self.batch, self.len_vision) if d in (64, 128, 288) else None
         self._versions = tuple(p._version for p in bridge.parameters())
         self._bridge = bridge
+        # per-position rows of block 0's cross-attention sub-layer output (see the module docstring)
+        self.max_positions = int(max_positions)
+        self.x1 = (torch.empty((self.batch, self.max_positions, bridge.language_dim), device=self.kv.device,
+                               dtype=torch.float32) if self.max_positions > 0 else None)
+        self.positions_filled = 0
+
+    def position_rows(self, length: int, cached_positions: int, device, dim: int):
+        """The row store for a forward over `length` text positions of which the first
+        `cached_positions` are reused, or None when the prefix is longer than the store (the caller then
+        computes every row). Raises if rows are asked for that were never written."""
+        if self.x1 is None or length > self.max_positions:
+            return None
+        k = int(cached_positions)
+        if not 0 <= k < length:
+            raise RuntimeError(f"cached_positions must be in [0, {length}) for a prefix of {length} positions, got {k}")
+        if k > self.positions_filled:
+            raise RuntimeError(f"cached_positions={k} but only {self.positions_filled} positions are cached")
+        if self.x1.device != device or self.x1.shape[-1] != dim:
+            raise RuntimeError("position rows live on another device / have another width than the text")
+        self.positions_filled = length
+        return self.x1
 
     @property
     def nbytes(self) -> int:
