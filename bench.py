@@ -643,10 +643,16 @@ def bench_fused_ce(dev, peaks) -> dict:
         out[name] = e0.elapsed_time(e1) / reps
     nbytes = 3.0 * rows * V * 4
     achieved = nbytes / (out["fused"] * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_ncu_ce_summary.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f)["summary"]["dram_bytes_fwd_plus_bwd"]
+        traffic_src = "profiles/r01_ncu_ce_summary.json: dram__bytes_read.sum + dram__bytes_write.sum, forward + backward launches"
     return {"metric": "cross-entropy fwd+bwd over [1024, 256000] fp32 logits", "ms": out["fused"], "torch_ms": out["torch"],
             "roofline": {"bound": "hbm", "kernel": "ce_fwd_kernel + ce_bwd_kernel", "achieved": achieved,
                          "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"],
-                         "algorithmic_bytes": nbytes, "traffic": None},
+                         "algorithmic_bytes": nbytes, "traffic": traffic, "traffic_source": traffic_src},
             "note": "inputs (2.1 GB with the gradient) exceed the 126 MB L2; includes the autograd node overhead"}
 
 
