@@ -192,7 +192,7 @@ def run_reference_arm(args) -> int:
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -548,7 +548,7 @@ def run_b200_arm(args) -> int:
             v, ms, cores, sample = cpu_bridge_samples_per_s(steps=3, warmup=1, budget_s=25.0)
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample,
                                     "ms_per_step": ms}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -753,6 +753,29 @@ def bench_decode(model, dev, peaks, _lib) -> dict:
     }
 
 
+_JSON_FD = None
+
+
+def own_stdout() -> None:
+    """The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner to
+    fd 1 on some boxes), so fd 1 is pointed at stderr for the rest of the run and the JSON line goes to a
+    private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -783,6 +806,7 @@ def main() -> int:
         global B_PER_GPU, N_VIS, WORKLOAD
         B_PER_GPU, N_VIS, WORKLOAD = 16, 1370, "C5"
         args.no_decode = args.no_train_step = args.no_cpu_baseline = True
+    own_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_b200_arm(args)
