@@ -732,6 +732,13 @@ def bench_decode(model, dev, peaks, _lib) -> dict:
     cross_ms = sum(ms_ for name, ms_ in entries if name in ("attn_decode_packed", "attn_decode_tc"))
     bytes_total = sum(decode_bytes_per_step(DEC_B, s, N_VIS, position_rows=True) for s in range(1, DEC_STEPS + 1))
     achieved = bytes_total / (cross_ms * 1e-3) / 1e9 if cross_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_ncu_decode_packed_summary.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f)["summary"]["dram_bytes_per_launch_len_q_1"]
+        traffic_src = ("profiles/r01_ncu_decode_packed_summary.json: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                       "1-position launch (ncu --set full); algorithmic bytes of that launch: 76.1 MB")
     return {
         "metric": "caption decode tokens/sec (bridge-only loop, cached vision K/V)",
         "value": DEC_B * DEC_STEPS / (ms * 1e-3), "unit": "tokens/s", "ms_per_caption_batch": ms,
@@ -743,8 +750,8 @@ def bench_decode(model, dev, peaks, _lib) -> dict:
                    "cross-attention rows cached per text position, everything from block 0's non-causal "
                    "self-attention on recomputed over the prefix every step"),
         "roofline": {"bound": "hbm", "kernel": "attn_decode_kernel<288, packed> for <= 32 positions (all 64 block-0 launches: 1 position each), attn_decode_tc_kernel<288> above (the 128 cross-attention launches)", "achieved": achieved,
-                     "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": None,
-                     "algorithmic_bytes_total": bytes_total, "kernel_ms_total": cross_ms,
+                     "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": traffic,
+                     "traffic_source": traffic_src, "algorithmic_bytes_total": bytes_total, "kernel_ms_total": cross_ms,
                      "note": ("event-timed between eager launches. Graph-timed per launch (profiles/r01_exp_decode_v3.jsonl, "
                               "r01_exp_decode_tc_v4.jsonl): 17-19 us (65-68 % of the HBM peak) up to 16 positions, 24-25 us up to 32 "
                               "(legacy HMMA pipe), 28-31 us (47 %) for 33-64 on the tcgen05 kernel, whose M=64 MMAs cost >= 47 "
