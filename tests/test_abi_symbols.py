@@ -55,6 +55,16 @@ def test_argument_validation_needs_no_gpu(lib):
     assert lib.b200b_layernorm_fwd(None, None, None, None, None, None, 4, 8, 1e-5, None) == -3
     lib.b200b_bridge_block_saved_bytes.restype = ctypes.c_size_t
     assert lib.b200b_bridge_block_saved_bytes(None) == 0
+    # fused cross-entropy: null pointers, a dtype that is neither f32 nor bf16, a shift length that does not divide the rows
+    i64, vp = ctypes.c_int64, ctypes.c_void_p
+    lib.b200b_cross_entropy_fwd.argtypes = [vp, ctypes.c_int, i64, vp, i64, i64, i64, i64, vp, vp, vp, vp]
+    assert lib.b200b_cross_entropy_fwd(None, 0, 8, None, 4, 8, -100, 0, None, None, None, None) == -3
+    buf = ctypes.create_string_buffer(64)                   # a non-null pointer that is never dereferenced on the host
+    addr = ctypes.addressof(buf)
+    assert lib.b200b_cross_entropy_fwd(addr, 2, 8, addr, 4, 8, -100, 0, addr, addr, addr, None) == -3
+    assert b"dtype" in lib.b200b_last_error()
+    assert lib.b200b_cross_entropy_fwd(addr, 0, 8, addr, 4, 8, -100, 3, addr, addr, addr, None) == -1    # B200B_ERR_SHAPE
+    assert lib.b200b_cross_entropy_fwd(addr, 0, 4, addr, 4, 8, -100, 0, addr, addr, addr, None) == -3    # ld < vocab
 
 
 def test_product_fails_loudly_without_cuda():
