@@ -537,6 +537,12 @@ def run_b200_arm(args) -> int:
                 line["train_step"] = bench_train_step(model, step, vision_d, text_d, args.steps)
             except Exception as e:  # noqa: BLE001
                 line["train_step"] = {"error": repr(e)[:300]}
+        # ---- the same step through PyTorch's stock kernels on the same GPU (comparison), N=1 only ------
+        if world == 1 and not args.no_train_step:
+            try:
+                line["torch_library"] = bench_torch_library(model, vision_d, text_d, args.steps)
+            except Exception as e:  # noqa: BLE001
+                line["torch_library"] = {"error": repr(e)[:300]}
         # ---- fused cross-entropy over the LM logits, N=1 only ------------------
         if world == 1 and not args.no_train_step:
             try:
@@ -600,6 +606,74 @@ def bench_train_step(model, step, vision_d, text_d, steps: int) -> dict:
             "optimizer_hbm_GBs": (158160384 * 32 + model._layout.n_weights * 2) / (ms_opt * 1e-3) / 1e9,
             "launch_mode": "eager", "grad_norm_last": float(opt.last_grad_norm),
             "steps_that_gathered_grads": opt.gather_steps}
+
+
+def torch_library_forward(sd, vision, text, num_blocks: int, heads_cross: int, heads_self: int, p: float, training: bool):
+    """The bridge arithmetic spelled with PyTorch's stock operators (F.linear -> cuBLASLt, F.layer_norm,
+    F.scaled_dot_product_attention, F.gelu, F.dropout) over a BridgeLite `state_dict`: what the same GPU does
+    for this workload WITHOUT this repository's kernels. Used only as a timed comparison (`torch_library` in the
+    bench line) and checked against the oracle on the CPU (tests/test_bench_contract.py)."""
+    import torch.nn.functional as F
+
+    def lin(x, name):
+        return F.linear(x, sd[name + ".weight"], sd[name + ".bias"])
+
+    def norm(x, name):
+        return F.layer_norm(x, x.shape[-1:], sd[name + ".weight"], sd[name + ".bias"], 1e-5)
+
+    def mha(q, k, v, h):
+        def split(t):
+            return t.view(t.shape[0], t.shape[1], h, t.shape[2] // h).transpose(1, 2)
+        o = F.scaled_dot_product_attention(split(q), split(k), split(v), dropout_p=p if training else 0.0)
+        return o.transpose(1, 2).reshape(q.shape)
+
+    x = text
+    for i in range(num_blocks):
+        b = f"bridge_blocks.{i}."
+        xn = norm(x, b + "ln_cross")
+        c = b + "cross_attention."
+        x = x + lin(mha(lin(xn, c + "w_q"), lin(vision, c + "w_k"), lin(vision, c + "w_v"), heads_cross), c + "w_o")
+        xn = norm(x, b + "ln_self")
+        a = b + "self_attention."
+        x = x + lin(mha(lin(xn, a + "w_q"), lin(xn, a + "w_k"), lin(xn, a + "w_v"), heads_self), a + "w_o")
+        xn = norm(x, b + "ln_ffn")
+        hidden = F.dropout(F.gelu(lin(xn, b + "ffn.0")), p, training)
+        x = x + F.dropout(lin(hidden, b + "ffn.3"), p, training)
+    return x
+
+
+def bench_torch_library(model, vision_d, text_d, steps: int) -> dict:
+    """The same fwd+bwd step on the same GPU through PyTorch's own kernels under torch.autocast(bfloat16), eager
+    launches -- how the reference module itself would run on this B200. A comparison line, not a target."""
+    import torch
+
+    sd = {k: v.detach().clone().requires_grad_() for k, v in model.state_dict().items()}
+    leaves = list(sd.values())
+
+    def step():
+        for t in leaves:
+            t.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = torch_library_forward(sd, vision_d, text_d, N_BLOCKS, H_CROSS, H_SELF, DROPOUT, True)
+        loss = y.float().square().mean()
+        loss.backward()
+        return loss
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    n = max(5, min(20, steps))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return {"metric": "bridge fwd+bwd samples/sec through PyTorch's stock kernels on the same GPU", "value": B_PER_GPU / (ms * 1e-3),
+            "unit": "samples/s", "ms_per_step": ms, "steps": n,
+            "how": f"torch {torch.__version__} eager, torch.autocast(bfloat16): F.linear (cuBLASLt), F.layer_norm, "
+                   "F.scaled_dot_product_attention, F.gelu, F.dropout; same weights, inputs, dropout p, loss"}
 
 
 def bench_fused_ce(dev, peaks) -> dict:

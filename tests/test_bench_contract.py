@@ -37,3 +37,29 @@ def test_algorithmic_work_figures():
     assert bench.decode_bytes_per_step(B, 64, Nv, position_rows=True) == 2 * kv + 2 * B * D * 2 * (1 + 64)
     total = sum(bench.decode_bytes_per_step(B, s, Nv) for s in range(1, 65))
     assert abs(total / 1e9 - 10.93) < 0.01
+
+
+def test_torch_library_arm_is_the_same_arithmetic():
+    """bench.py's `torch_library` comparison (PyTorch's stock operators) computes the bridge: equal to the
+    oracle in fp32 on the CPU at small dims, forward and gradients."""
+    import torch
+
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import bridge_oracle as O
+
+    sd = O.init_state_dict(3, vision_dim=32, language_dim=64, num_blocks=2)
+    g = torch.Generator().manual_seed(1)
+    for k in sd:                                             # non-trivial biases and LayerNorm affine
+        if k.endswith("bias") or "ln_" in k:
+            sd[k] = sd[k] + 0.1 * torch.randn(sd[k].shape, generator=g)
+    vision, text = torch.randn(2, 9, 32, generator=g), torch.randn(2, 5, 64, generator=g)
+    y_ref, _, dtext_ref, g_ref = O.bridge_loss_and_grads(sd, vision, text, heads_cross=2, heads_self=4)
+    leaves = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    t = text.clone().requires_grad_()
+    y = bench.torch_library_forward(leaves, vision, t, 2, 2, 4, 0.1, False)
+    y.square().mean().backward()
+    assert torch.allclose(y, y_ref, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(t.grad, dtext_ref, rtol=1e-3, atol=1e-7)
+    for k in sd:
+        assert torch.allclose(leaves[k].grad, g_ref[k], rtol=1e-3, atol=1e-6), k
