@@ -137,14 +137,45 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference bridge on the host cores
 # ------------------------------------------------------------------------------------------------
+def _cpu_oracle():
+    """The CPU restatement of the reference module: test infrastructure, imported by the CPU legs only."""
+    from oracle import bridge_oracle as O
+
+    return O
+
+
+def cpu_decode_tokens_per_s(new_tokens: int = 16):
+    """CPU baseline of caption decode: the reference's loop shape -- batch 1, every step
+    re-runs the bridge on the whole prefix INCLUDING the K/V projections of the unchanged image
+    (full_model.py:241-256) -- bridge only, fp32, `new_tokens` steps from a 1-token prefix."""
+    import torch
+
+    O = _cpu_oracle()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.init_state_dict(0)
+    g = torch.Generator().manual_seed(4321)
+    vision = torch.randn(1, N_VIS, D_VIS, generator=g)
+    text = torch.randn(1, new_tokens, D_LANG, generator=g)
+    with torch.no_grad():
+        O.bridge_forward(sd, vision, text[:, :1], num_blocks=N_BLOCKS, heads_cross=H_CROSS, heads_self=H_SELF)   # warm-up
+        t0 = time.perf_counter()
+        for s in range(1, new_tokens + 1):
+            O.bridge_forward(sd, vision, text[:, :s], num_blocks=N_BLOCKS, heads_cross=H_CROSS, heads_self=H_SELF)
+        dt = time.perf_counter() - t0
+    return {"value": new_tokens / dt, "unit": "tokens/s", "cores": cores, "kind": "port",
+            "sample": f"oracle port, batch 1, {new_tokens} new tokens, prefix and K/V projections recomputed every step "
+                      f"(the reference's loop), fp32, bridge only; batch-1 latency-shaped: tokens/s of {DEC_B} images "
+                      f"decoded one after the other is the same figure"}
+
+
 def cpu_bridge_samples_per_s(steps: int, warmup: int, budget_s: float):
     """Times oracle fwd+bwd (the CPU restatement of the reference module) at config C2's shape.
     If a full batch-8 step would blow the time budget, a smaller batch is used as the sample and
     samples/s is computed from it (samples are independent in the bridge)."""
     import torch
 
-    from oracle import bridge_oracle as O
-
+    O = _cpu_oracle()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = O.init_state_dict(0)
@@ -554,6 +585,11 @@ def run_b200_arm(args) -> int:
             v, ms, cores, sample = cpu_bridge_samples_per_s(steps=3, warmup=1, budget_s=25.0)
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample,
                                     "ms_per_step": ms}
+            if isinstance(line.get("decode"), dict) and "error" not in line["decode"]:
+                try:
+                    line["decode"]["cpu_baseline"] = cpu_decode_tokens_per_s()
+                except Exception as e:  # noqa: BLE001
+                    line["decode"]["cpu_baseline"] = {"error": repr(e)[:200]}
         emit(line)
     if world > 1:
         dist.barrier()

@@ -35,7 +35,12 @@ def test_bench_uses_oracle_only_in_cpu_legs():
     src = open(os.path.join(ROOT, "bench.py")).read()
     uses = [m.start() for m in re.finditer(r"from oracle import", src)]
     assert len(uses) == 1
-    # the single import sits inside the CPU-baseline function
+    # the single import sits inside _cpu_oracle(), which only the CPU legs (functions named cpu_*) call
     head = src[:uses[0]]
-    assert head.rfind("def cpu_bridge_samples_per_s") > head.rfind("def run_b200_arm")
+    assert head.rfind("def _cpu_oracle") == max(m.start() for m in re.finditer(r"^def \w+", head, flags=re.M))
+    for m in re.finditer(r"_cpu_oracle\(\)", src):
+        if src[m.start() - 4:m.start()] == "def ":
+            continue
+        enclosing = re.findall(r"^def (\w+)", src[:m.start()], flags=re.M)[-1]
+        assert enclosing.startswith("cpu_"), enclosing
     assert "/root/reference" not in src
