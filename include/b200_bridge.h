@@ -446,15 +446,6 @@ int b200b_allreduce_nvls(const b200b_nvls_comm* comm, int dtype, int64_t byte_of
 void b200b_set_sm_limit(int sms);
 int b200b_get_sm_limit(void);
 
-/* Diagnostic, not part of the bridge path (csrc/probe_tcgen05.cu): one CTA computes a[m,k] b[n,k]^T with
- * tcgen05.mma on operands it lays out in shared memory with the given swizzle width (32 / 64 / 128 bytes,
- * K-major) and dumps all 128 TMEM lanes x n columns of the accumulator to `dump` (fp32 [128, n]).
- * m in {64, 128}; n % 16 == 0, 16 <= n <= 256; k a multiple of swizzle_bytes / 2. With reps > 0 the MMA sequence is
- * first issued reps times into a scratch accumulator and cycles2[0..1] (device, int64) receive the SM clock cycles spent
- * issuing and until completion. */
-int b200b_probe_umma(const void* a, const void* b, float* dump, int m, int n, int k, int swizzle_bytes,
-                     int reps, long long* cycles2, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

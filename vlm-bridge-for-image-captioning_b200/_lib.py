@@ -144,9 +144,6 @@ def _declare(lib) -> None:
     lib.b200b_cross_entropy_bwd.restype = C.c_int
     lib.b200b_cross_entropy_bwd.argtypes = ([C.c_void_p, C.c_int, C.c_int64, C.c_void_p] + [C.c_int64] * 4 +
                                             [C.c_void_p] * 4 + [C.c_int64, C.c_void_p])
-    lib.b200b_probe_umma.restype = C.c_int
-    lib.b200b_probe_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                     C.c_void_p, C.c_void_p]
     lib.b200b_set_sm_limit.restype = None
     lib.b200b_set_sm_limit.argtypes = [C.c_int]
     lib.b200b_get_sm_limit.restype = C.c_int

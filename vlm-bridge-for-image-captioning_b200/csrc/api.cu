@@ -84,6 +84,76 @@ int device_sm_count(int* out) {
   return B200B_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tmap_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+struct HeadsMapKey {
+  const void* base;
+  long long ld;
+  int head_dim, heads, rows, batch, box_rows;
+  bool operator==(const HeadsMapKey& o) const {
+    return base == o.base && ld == o.ld && head_dim == o.head_dim && heads == o.heads && rows == o.rows &&
+           batch == o.batch && box_rows == o.box_rows;
+  }
+};
+struct HeadsMapEntry {
+  HeadsMapKey key;
+  CUtensorMap map;
+  bool used;
+};
+static std::mutex g_tmap_mu;
+static HeadsMapEntry g_tmap_cache[128];
+static unsigned g_tmap_next = 0;
+
+int make_tmap_heads_sw64(CUtensorMap* tm, const void* base, long long ld_elems, int head_dim, int heads, int rows,
+                         int batch, int box_rows) {
+  const HeadsMapKey key{base, ld_elems, head_dim, heads, rows, batch, box_rows};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    for (auto& e : g_tmap_cache)
+      if (e.used && e.key == key) {
+        *tm = e.map;
+        return B200B_OK;
+      }
+  }
+  EncodeTiledFn fn = tmap_encode_fn();
+  if (fn == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled not available from the driver");
+    return B200B_ERR_DRIVER;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)head_dim, (cuuint64_t)heads, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[3] = {(cuuint64_t)head_dim * 2, (cuuint64_t)ld_elems * 2, (cuuint64_t)rows * ld_elems * 2};
+  cuuint32_t box[4] = {32, 1, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (head slices) failed (%d): base=%p ld=%lld head_dim=%d heads=%d rows=%d "
+                   "batch=%d box_rows=%d", (int)r, base, ld_elems, head_dim, heads, rows, batch, box_rows);
+    return B200B_ERR_TENSORMAP;
+  }
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  HeadsMapEntry& e = g_tmap_cache[g_tmap_next++ % 128];
+  e.key = key;
+  e.map = *tm;
+  e.used = true;
+  return B200B_OK;
+}
+
 }  // namespace b200b
 
 extern "C" int b200b_abi_version(void) { return B200B_ABI_VERSION; }

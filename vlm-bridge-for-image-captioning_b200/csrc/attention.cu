@@ -425,11 +425,13 @@ __global__ void __launch_bounds__(256, 2) attn_decode_kernel(const AttnParams p)
       }
       mbar_wait(&full_bar[st], (uint32_t)((t / NS) & 1));
       const uint32_t st_base = smem_u32(ring + (size_t)st * Cfg::kStageElems);
-      if (p.Lkp < 0) {  // DEBUG (B200B_DECODE_DEBUG=1): copy-only
+#ifdef B200B_DIAG
+      if (p.Lkp < 0) {  // diagnostics build only (B200B_DECODE_DEBUG=1): copy-only
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[st]);
         continue;
       }
+#endif
 
       // partial S = Q[:, half] K[:, half]^T; two accumulator sets shorten the dependent-MMA chains
       float s[2][4], s2[2][4];
@@ -871,9 +873,11 @@ static int launch_decode(const AttnParams& p, cudaStream_t stream) {
   }
   const int nrg = (min(64, p.Lq) + 15) / 16;
   dim3 grid((p.Lq + 63) / 64, p.H, p.B);
-  static const int dbg = [] { const char* e = getenv("B200B_DECODE_DEBUG"); return e ? atoi(e) : 0; }();
   AttnParams pp = p;
+#ifdef B200B_DIAG
+  static const int dbg = [] { const char* e = getenv("B200B_DECODE_DEBUG"); return e ? atoi(e) : 0; }();
   if (dbg & 1) pp.Lkp = -1;
+#endif
   launch_pdl(kPdlAttn, attn_decode_kernel<HD, PACKED>, grid, dim3(256), Cfg::smem_bytes(nrg), stream, pp);
   return check_launch(PACKED ? "attn_decode_packed" : "attn_decode", stream);
 }

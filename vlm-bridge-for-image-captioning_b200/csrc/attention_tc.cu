@@ -5,7 +5,7 @@
 // decode cross-attention (full_model.py:241-261 -> bridge_module.py:122-139 on the cached vision K/V)
 // memory-bound for every prefix length up to 64.
 //
-// Layout facts this kernel rests on were measured with csrc/probe_tcgen05.cu on B200:
+// Layout facts this kernel rests on were measured with a one-CTA probe on B200 (now tests/gpu_checks/probe_umma_layouts.cu; profiles/r01_probe_tcgen05.jsonl):
 //   * 32-byte-swizzle K-major operands (descriptor layout code 6) work for any K that is a multiple of
 //     16 -- head dim 288 = 18 chunks of 16 -- with SBO = 256 B (8 rows x 32 B) and one k-step per chunk;
 //   * an M = 64 accumulator (cta_group::1) keeps row r in TMEM lane 32*(r/16) + r%16, i.e. warp w finds
@@ -54,25 +54,6 @@ __host__ __device__ __forceinline__ uint32_t sw32_offset(int row, int k, int row
          ((((uint32_t)(k >> 3) & 1u) ^ (((uint32_t)row >> 2) & 1u)) << 4) + ((uint32_t)k & 7u) * 2u;
 }
 
-__device__ __forceinline__ void tmem_ld_32x32_x16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 struct TcParams {
   const __nv_bfloat16* q; long long ldq;
   const uint8_t* kv;            // this block's first (image 0, head 0) tile; see strides
@@ -81,7 +62,7 @@ struct TcParams {
   float* lse2;                  // [B, H, Lq] or null
   int B, H, Lq, Lk;
   float scale_log2;
-  int debug_copy_only;          // B200B_DECODE_DEBUG=1: stream the tiles, skip MMAs and softmax (diagnostics)
+  int debug_copy_only;          // -DB200B_DIAG builds only: stream the tiles, skip MMAs and softmax
 };
 
 template <int HD>
@@ -181,6 +162,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_decode_tc_kernel(const TcP
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t tmem_o = tmem_base + Cfg::kOCol;
 
+#ifdef B200B_DIAG
   if (p.debug_copy_only) {
     if (warp == 4) {
       for (int t = 0; t < nt; ++t) {
@@ -189,7 +171,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_decode_tc_kernel(const TcP
         __syncwarp();
       }
     }
-  } else if (warp == 4) {
+  } else
+#endif
+  if (warp == 4) {
     // ---------------------------- control warp: MMA issue and K/V refills ----------------------------
     const uint64_t q_desc0 = umma_desc_sw32(smem_u32(q_img));
     const uint64_t p_desc0 = umma_desc_sw32(smem_u32(p_img));
@@ -502,8 +486,10 @@ extern "C" int b200b_attention_decode_tc(const void* q, int64_t ldq, const void*
   p.lse2 = lse;
   p.B = batch; p.H = heads; p.Lq = len_q; p.Lk = len_k;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
+#ifdef B200B_DIAG
   static const int dbg = [] { const char* e = getenv("B200B_DECODE_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug_copy_only = dbg & 1;
+#endif
   switch (head_dim) {
     case 64: return launch_tc<64>(p, stream);
     case 128: return launch_tc<128>(p, stream);

@@ -469,6 +469,81 @@ __device__ __forceinline__ void mbar_arrive_cluster_a(uint32_t cluster_addr) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// tcgen05 pieces shared by the attention kernels (attention_tc.cu, attention_train_tc.cu)
+// ----------------------------------------------------------------------------------------------
+// TMEM <-> registers, this warp's 32 lanes x 16 consecutive 32-bit columns (thread i = lane i)
+__device__ __forceinline__ void tmem_ld_32x32_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand is read from tensor memory (lane = row, 32-bit
+// column c holds the bf16 elements 2c, 2c+1 of the row; one K = 16 step reads 8 columns). Measured with
+// tests/gpu_checks/probe_umma_layouts.cu on B200 (profiles/r02_probe_umma_layouts.jsonl).
+__device__ __forceinline__ void umma_bf16_tmem_a(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Shared-memory operand tiles of the training attention kernels: [cols / 32 chunks][R rows][64 bytes],
+// 64-byte swizzle (16-byte units XORed with (row >> 1) & 3), which is what a TMA box {32 elements, R rows}
+// with CU_TENSOR_MAP_SWIZZLE_64B writes per chunk. One tile serves both operand forms (probe-verified):
+//   K-major  (rows = M or N index, contraction along the columns): k-step ks of 16 columns starts at
+//            chunk ks / 2, + 32 bytes for odd ks; SBO = 512 (8 rows x 64 B)
+//   MN-major (columns = M or N index, contraction along the rows): the operand starts at chunk c0, k-step
+//            kc of 16 rows is + 1024 bytes; LBO = R * 64 (chunk stride), SBO = 512
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(512u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;  // SWIZZLE_64B
+  return d;
+}
+__device__ __forceinline__ uint64_t desc_sw64_kmajor(uint32_t tile, uint32_t rows, int ks) {
+  return umma_desc_sw64(tile + (uint32_t)(ks >> 1) * rows * 64u + (uint32_t)(ks & 1) * 32u, 16u);
+}
+__device__ __forceinline__ uint64_t desc_sw64_mnmajor(uint32_t tile, uint32_t rows, int chunk0, int kc) {
+  return umma_desc_sw64(tile + (uint32_t)chunk0 * rows * 64u + (uint32_t)kc * 1024u, rows * 64u);
+}
+// byte offset of the 16-byte unit holding columns [8u', 8u'+8) (u' = col / 8) of `row` in such a tile
+__device__ __forceinline__ uint32_t sw64_unit_offset(uint32_t row, uint32_t col, uint32_t rows) {
+  return (col >> 5) * rows * 64u + row * 64u + ((((col >> 3) & 3u) ^ ((row >> 1) & 3u)) << 4);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // warp-level mma.sync helpers (used by the attention kernels): m16n8k16 bf16 -> fp32
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma_m16n8k16(float (&c)[4], const uint32_t (&a)[4],

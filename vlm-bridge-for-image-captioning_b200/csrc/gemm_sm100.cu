@@ -45,7 +45,6 @@ struct GemmKernelParams {
   float beta;
   DropoutCfg drop;
   uint32_t drop_stream;
-  int debug_mode;  // bring-up experiments only: 1 = producer skips the TMA loads, 2 = MMA thread skips the MMAs
 };
 
 constexpr int kBlockM = 128;
@@ -356,25 +355,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           const uint32_t sa = smem0 + (uint32_t)stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           const uint32_t fb = full0 + 8u * stage;
-          if (p.debug_mode == 1) {
-            mbar_arrive_a(fb);
+          mbar_arrive_expect_tx_a(fb, Cfg::kStageBytes);
+          const int k_idx = kb * kBlockK;
+          if constexpr (!A_MN) {
+            tma_load_2d_a(sa, &tm_a, fb, k_idx, m_idx);  // box {64 k, 128 rows}
           } else {
-            mbar_arrive_expect_tx_a(fb, Cfg::kStageBytes);
-            const int k_idx = kb * kBlockK;
-            if constexpr (!A_MN) {
-              tma_load_2d_a(sa, &tm_a, fb, k_idx, m_idx);  // box {64 k, 128 rows}
-            } else {
 #pragma unroll
-              for (int j = 0; j < kBlockM / 64; ++j)       // box {64 m, 64 k} per atom
-                tma_load_2d_a(sa + j * 8192, &tm_a, fb, m_idx + 64 * j, k_idx);
-            }
-            if constexpr (!B_MN) {
-              tma_load_2d_a(sb, &tm_b, fb, k_idx, n_idx);  // box {64 k, BLOCK_N rows}
-            } else {
+            for (int j = 0; j < kBlockM / 64; ++j)       // box {64 m, 64 k} per atom
+              tma_load_2d_a(sa + j * 8192, &tm_a, fb, m_idx + 64 * j, k_idx);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_a(sb, &tm_b, fb, k_idx, n_idx);  // box {64 k, BLOCK_N rows}
+          } else {
 #pragma unroll
-              for (int j = 0; j < BLOCK_N / 64; ++j)
-                tma_load_2d_a(sb + j * 8192, &tm_b, fb, n_idx + 64 * j, k_idx);
-            }
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d_a(sb + j * 8192, &tm_b, fb, n_idx + 64 * j, k_idx);
           }
         }
         __syncwarp();
@@ -403,12 +398,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         tc_fence_after();
         if (elect_one()) {
           const uint32_t soff16 = ((uint32_t)stage * Cfg::kStageBytes) >> 4;
-          if (p.debug_mode != 2) {
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              umma_bf16(d_tmem, desc_with_lo(adesc0, soff16 + k * DescConsts<A_MN>::kKStep16),
-                        desc_with_lo(bdesc0, soff16 + k * DescConsts<B_MN>::kKStep16), idesc, (kb | k) != 0 ? 1u : 0u);
-            }
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            umma_bf16(d_tmem, desc_with_lo(adesc0, soff16 + k * DescConsts<A_MN>::kKStep16),
+                      desc_with_lo(bdesc0, soff16 + k * DescConsts<B_MN>::kKStep16), idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit_a(empty0 + 8u * stage);                              // frees the smem stage
           if (kb == p.num_k_blocks - 1) umma_commit_a(tfull0 + 8u * acc);  // accumulator ready
@@ -848,8 +841,6 @@ extern "C" int b200b_gemm(const b200b_gemm_args* a, void* stream_) {
   p.beta = a->beta;
   p.drop_stream = a->dropout_stream;
   p.drop = make_dropout_cfg(a->dropout_p, a->seed, &p.drop_stream);
-  static const int debug_mode = [] { const char* e = getenv("B200B_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
-  p.debug_mode = debug_mode;
 
   const long long tiles = (long long)p.num_m_blocks * p.num_n_blocks;
   if (pair) {

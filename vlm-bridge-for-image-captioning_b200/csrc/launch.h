@@ -16,6 +16,14 @@ int check_launch(const char* what, cudaStream_t stream);
 // SM count of the current device (cached per device); fails on non-sm_100 devices
 int device_sm_count(int* out);
 
+// Tensor map of a bf16 row-major matrix [batch * rows, ld] read as per-head slices of `head_dim` columns:
+// 4-D {head_dim, heads, rows, batch}, box {32 elements, 1, box_rows, 1}, 64-byte swizzle, out-of-range rows
+// and columns read as zeros. A box lands in shared memory as [box_rows][64 B] (see common.cuh, "operand
+// tiles of the training attention kernels"). Maps are cached by their arguments (the driver call costs
+// about a microsecond and a step builds the same few dozen maps every time).
+int make_tmap_heads_sw64(CUtensorMap* tm, const void* base, long long ld_elems, int head_dim, int heads, int rows,
+                         int batch, int box_rows);
+
 // Which kernel families are launched with programmatic stream serialization: bit mask from the
 // environment variable B200B_PDL (1 = GEMMs, 2 = attention, 4 = row / column / cast kernels).
 enum { kPdlGemm = 1, kPdlAttn = 2, kPdlRows = 4 };
