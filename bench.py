@@ -169,23 +169,52 @@ def cpu_decode_tokens_per_s(new_tokens: int = 16):
                       f"decoded one after the other is the same figure"}
 
 
+def _cpu_reference_module():
+    """The UNMODIFIED reference bridge_module.py, when oracle/make_ref.py has copied the reference package to
+    oracle/_ref/ (git-ignored, travels to the GPU box); None otherwise."""
+    try:
+        from oracle import make_ref
+        return make_ref.load_reference_bridge_module()
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def cpu_bridge_samples_per_s(steps: int, warmup: int, budget_s: float):
-    """Times oracle fwd+bwd (the CPU restatement of the reference module) at config C2's shape.
+    """Times the reference's own CPU implementation of the path at config C2's shape on the host cores: the
+    unmodified reference `BridgeLite` (oracle/_ref, train mode, dropout 0.1, fp32 -- `kind` "reference") when the
+    copy is present, else the oracle port (eval mode: the port has no dropout -- `kind` "port").
     If a full batch-8 step would blow the time budget, a smaller batch is used as the sample and
     samples/s is computed from it (samples are independent in the bridge)."""
     import torch
 
-    O = _cpu_oracle()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = O.init_state_dict(0)
     g = torch.Generator().manual_seed(1234)
+    ref = _cpu_reference_module()
+    if ref is not None:
+        torch.manual_seed(0)
+        m = ref.BridgeLite(vision_dim=D_VIS, language_dim=D_LANG, num_blocks=N_BLOCKS, num_heads_cross=H_CROSS,
+                           num_heads_self=H_SELF, dropout=DROPOUT).train()
+        params = list(m.parameters())
+        kind = "reference"
+        what = (f"UNMODIFIED reference BridgeLite (oracle/_ref/vlm_bridge/model_architecture/bridge_module.py) fwd+bwd, "
+                f"fp32, train mode dropout {DROPOUT}")
+
+        def step(v, t):
+            for p in params:
+                p.grad = None
+            m(v, t).square().mean().backward()
+    else:
+        O = _cpu_oracle()
+        sd = O.init_state_dict(0)
+        kind = "port"
+        what = "oracle port of BridgeLite fwd+bwd (fp32, EVAL mode: the port has no dropout)"
+
+        def step(v, t):
+            O.bridge_loss_and_grads(sd, v, t, num_blocks=N_BLOCKS, heads_cross=H_CROSS, heads_self=H_SELF)
 
     def make(b):
         return torch.randn(b, N_VIS, D_VIS, generator=g), torch.randn(b, L_TEXT, D_LANG, generator=g)
-
-    def step(v, t):
-        O.bridge_loss_and_grads(sd, v, t, num_blocks=N_BLOCKS, heads_cross=H_CROSS, heads_self=H_SELF)
 
     b = B_PER_GPU
     v, t = make(b)
@@ -204,22 +233,22 @@ def cpu_bridge_samples_per_s(steps: int, warmup: int, budget_s: float):
         step(v, t)
         times.append(time.perf_counter() - t0)
     per_step = sum(times) / len(times)
-    sample = (f"oracle port of BridgeLite fwd+bwd (fp32, eval/no dropout), batch {b} x L{L_TEXT} x Nv{N_VIS}, "
+    sample = (f"{what}, batch {b} x L{L_TEXT} x Nv{N_VIS}, "
               f"{steps} timed steps after {warmup} warm-up, torch CPU {torch.__version__}, {cores} threads")
-    return b / per_step, per_step * 1e3, cores, sample
+    return b / per_step, per_step * 1e3, cores, sample, kind
 
 
 def run_reference_arm(args) -> int:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    value, ms, cores, sample = cpu_bridge_samples_per_s(args.steps, args.warmup, budget_s=200.0)
+    value, ms, cores, sample, kind = cpu_bridge_samples_per_s(args.steps, args.warmup, budget_s=200.0)
     line = {
         "impl": "reference", "metric": "bridge fwd+bwd samples/sec", "value": value, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -496,7 +525,47 @@ def run_b200_arm(args) -> int:
             trace = {"buckets": reducer.trace_report(), "backward_end_ms": round(reducer._t0.elapsed_time(bwd_end), 3)}
             reducer.trace = None
             sync_all()
-        line["dp"] = {"trace": trace,"allreduce": reducer.describe(), "bytes_per_step": reducer.bytes_per_step,
+        # ---- parity of the exchanged gradients at this N (untimed): eval mode (dropout off, so that the same
+        # masks are not needed twice); want = mean over ranks of the no-exchange gradients (all-gathered through
+        # NCCL in fp32); got = what every rank's .grad holds after a step with the exchange on, launched
+        # eagerly and as a replay of a freshly captured graph
+        def flat_grads():
+            return torch.cat([p.grad.detach().reshape(-1).float() for p in params])
+
+        model.eval()
+        model._bucket_hook = None
+        step(vision_d, text_d)
+        want = flat_grads().clone()
+        dist.all_reduce(want, op=dist.ReduceOp.SUM)
+        want /= world
+        model._bucket_hook = reducer
+        parity = {}
+        step(vision_d, text_d)
+        torch.cuda.synchronize()
+        parity["eager"] = float((flat_grads() - want).norm() / want.norm())
+        try:
+            from vlm_bridge_b200 import GraphedBridgeStep
+            gp = GraphedBridgeStep(model, lambda y: y.float().square().mean(), vision_d, text_d)
+            gp.replay()
+            gp.replay()
+            torch.cuda.synchronize()
+            parity["graph_replay"] = float((flat_grads() - want).norm() / want.norm())
+            del gp
+        except Exception as e:  # noqa: BLE001
+            parity["graph_replay"] = repr(e)[:200]
+        for p_ in params:
+            p_.grad = None
+        model.train()
+        pt = torch.tensor([v if isinstance(v, float) else float("nan") for v in (parity["eager"], parity["graph_replay"])],
+                          device=dev, dtype=torch.float64)
+        dist.all_reduce(pt, op=dist.ReduceOp.MAX)                  # worst rank
+        tol = 1.5e-2 if reducer.wgrad_bf16 else 1e-5
+        parity_line = {"eager": float(pt[0]), "graph_replay": float(pt[1]), "tolerance": tol,
+                       "ok": bool(float(pt[0]) <= tol and float(pt[1]) <= tol),
+                       "what": "max over ranks of |grad_exchanged - mean_r grad_r| / |mean_r grad_r| (Frobenius, all 158 M "
+                               "gradient elements), C2 shapes, eval mode; bf16 buckets round the weight gradients to bf16"}
+        sync_all()
+        line["dp"] = {"parity_rel_err": parity_line, "trace": trace, "allreduce": reducer.describe(), "bytes_per_step": reducer.bytes_per_step,
                       "ms_per_step_without_allreduce": float(t_local[0]) / args.steps,
                       "host_enqueue_ms_per_step_without_allreduce": host_ms_nodp,
                       "exposed_allreduce_ms": ms_step - float(t_local[0]) / args.steps}
@@ -543,9 +612,11 @@ def run_b200_arm(args) -> int:
             traffic_src = ("profiles/r01_ncu_gemm_step_v8.json: dram__bytes_read.sum + dram__bytes_write.sum of the 38 GEMM "
                            "launches of one step (ncu --set full), average per launch")
         line["roofline"] = {
-            "bound": "tensor", "kernel": "+".join(sorted(gemm_names)), "achieved": achieved, "peak": peaks["bf16_sustained"],
-            "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"], "frac_of_burst_peak": achieved / peaks["bf16_burst"],
-            "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)", "traffic": traffic,
+            "bound": "tensor", "kernel": "+".join(sorted(gemm_names)), "achieved": achieved, "peak": peaks["bf16_burst"],
+            "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"],
+            "frac_of_sustained_peak": achieved / peaks["bf16_sustained"], "peak_sustained": peaks["bf16_sustained"],
+            "peak_source": peaks["source"] + ", burst figure: the kernels are event-timed in a ~20 ms pass at full SM clock "
+                           "(the sustained figure was taken under a power cap at 1357 MHz)", "traffic": traffic,
             "traffic_unit": "bytes per launch (HBM; the roofline itself is the tensor pipe)", "traffic_source": traffic_src,
             "launches_per_step": gemm_launches,
             "avg_launch_ms": gemm_ms / max(1, gemm_launches),
@@ -582,8 +653,8 @@ def run_b200_arm(args) -> int:
                 line["fused_ce"] = {"error": repr(e)[:300]}
         # ---- CPU baseline beside it (N=1 only) ---------------------------------------------------
         if world == 1 and not args.no_cpu_baseline:
-            v, ms, cores, sample = cpu_bridge_samples_per_s(steps=3, warmup=1, budget_s=25.0)
-            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample,
+            v, ms, cores, sample, kind = cpu_bridge_samples_per_s(steps=3, warmup=1, budget_s=25.0)
+            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample,
                                     "ms_per_step": ms}
             if isinstance(line.get("decode"), dict) and "error" not in line["decode"]:
                 try:
@@ -679,36 +750,63 @@ def torch_library_forward(sd, vision, text, num_blocks: int, heads_cross: int, h
 
 
 def bench_torch_library(model, vision_d, text_d, steps: int) -> dict:
-    """The same fwd+bwd step on the same GPU through PyTorch's own kernels under torch.autocast(bfloat16), eager
-    launches -- how the reference module itself would run on this B200. A comparison line, not a target."""
+    """The same fwd+bwd step on the same GPU through PyTorch's own kernels under torch.autocast(bfloat16) -- how
+    the reference module itself would run on this B200. Timed twice: eager launches (what the reference's loop
+    does; may be host-bound) and as a replay of one captured CUDA graph (device time only: the like-for-like
+    figure against this repository's graph replay). A comparison line, not a target."""
     import torch
 
     sd = {k: v.detach().clone().requires_grad_() for k, v in model.state_dict().items()}
     leaves = list(sd.values())
 
-    def step():
-        for t in leaves:
-            t.grad = None
+    def step(set_none=True):
+        if set_none:
+            for t in leaves:
+                t.grad = None
         with torch.autocast("cuda", dtype=torch.bfloat16):
             y = torch_library_forward(sd, vision_d, text_d, N_BLOCKS, H_CROSS, H_SELF, DROPOUT, True)
         loss = y.float().square().mean()
         loss.backward()
         return loss
 
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
     n = max(5, min(20, steps))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
-    return {"metric": "bridge fwd+bwd samples/sec through PyTorch's stock kernels on the same GPU", "value": B_PER_GPU / (ms * 1e-3),
-            "unit": "samples/s", "ms_per_step": ms, "steps": n,
-            "how": f"torch {torch.__version__} eager, torch.autocast(bfloat16): F.linear (cuBLASLt), F.layer_norm, "
+    ms = timed(step, n)
+    ms_graph, graph_err = None, None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for t in leaves:
+            t.grad = None
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            step(set_none=False)          # grads are allocated from the graph's pool and overwritten per replay
+        ms_graph = timed(gr.replay, n)
+        del gr
+    except Exception as e:  # noqa: BLE001
+        graph_err = repr(e)[:200]
+        torch.cuda.synchronize()
+    best = min(ms, ms_graph) if ms_graph is not None else ms
+    return {"metric": "bridge fwd+bwd samples/sec through PyTorch's stock kernels on the same GPU", "value": B_PER_GPU / (best * 1e-3),
+            "unit": "samples/s", "ms_per_step": best, "steps": n,
+            "ms_per_step_by_launch_mode": {"eager": ms, "cuda graph replay": ms_graph, "graph_error": graph_err},
+            "how": f"torch {torch.__version__}, torch.autocast(bfloat16): F.linear (cuBLASLt), F.layer_norm, "
                    "F.scaled_dot_product_attention, F.gelu, F.dropout; same weights, inputs, dropout p, loss"}
 
 
@@ -766,82 +864,98 @@ def bench_fused_ce(dev, peaks) -> dict:
             "note": "inputs (2.1 GB with the gradient) exceed the 126 MB L2; includes the autograd node overhead"}
 
 
+def decode_gemm_flops(B: int, steps: int, Nv: int, position_rows: bool = True) -> float:
+    """Algorithmic FLOPs of the dense contractions of one caption batch (steps new tokens, prefix s = 1..steps):
+    the per-image K/V projection once, block 0's cross-attention projections once per position (position rows) or
+    once per position per step, everything else of both blocks over the whole prefix every step."""
+    D, Dv, F = D_LANG, D_VIS, 4 * D_LANG
+    per_row_cross = 2.0 * D * D * 2                       # w_q, w_o
+    per_row_rest = 2.0 * D * D * 4 + 4.0 * D * F          # self q,k,v,o + ffn
+    rows_all = B * steps * (steps + 1) / 2.0
+    rows_new = B * steps
+    total = N_BLOCKS * 2.0 * (B * Nv) * Dv * D * 2        # K and V of every block
+    total += per_row_cross * ((rows_new if position_rows else rows_all) + (N_BLOCKS - 1) * rows_all)
+    total += per_row_rest * N_BLOCKS * rows_all
+    return total
+
+
 def bench_decode(model, dev, peaks, _lib) -> dict:
-    """Config C4: greedy-decode-shaped loop, batch 32, 64 steps, prefix length s = 1..64, bridge only
-    (the frozen LM is outside the hot path). The per-image K/V are projected once and cached."""
+    """Config C4: batched greedy caption decode, batch 32, 64 new tokens, through `greedy_decode` itself (embed ->
+    bridge over the prefix -> read-out -> argmax -> append, ids read back). The frozen language model is outside
+    the hot path; a fixed embedding table and a fixed linear read-out (vocabulary 8192) stand in for it. Every
+    caption batch pays the per-image K/V projection + packing (`VisionKVCache` built, or refilled in place when
+    the step graphs are reused)."""
     import torch
 
-    from vlm_bridge_b200 import VisionKVCache
+    from vlm_bridge_b200 import DecodeStepGraphs, VisionKVCache, greedy_decode
 
     model.eval()
+    V = 8192
     g = torch.Generator().manual_seed(4321)
-    vision = torch.randn(DEC_B, N_VIS, D_VIS, generator=g).to(dev)
-    text = torch.randn(DEC_B, DEC_STEPS, D_LANG, generator=g).to(dev)
+    vision_h = torch.randn(DEC_B, N_VIS, D_VIS, generator=g).pin_memory()
+    vision = vision_h.to(dev)
+    embed = torch.randn(V, D_LANG, generator=g).to(dev)
+    head = (torch.randn(V, D_LANG, generator=g) / 48.0).to(dev)
+    ids_h = torch.empty((DEC_B, DEC_STEPS + 1), dtype=torch.long).pin_memory()
+    kw = dict(bos_token_id=2, eos_token_id=1, max_new_tokens=DEC_STEPS)
 
-    def loop(cache, graphs=None, rows=True):
-        # rows: block 0's cross-attention rows are kept per text position (computed for the new token only)
-        with torch.no_grad():
-            for s in range(1, DEC_STEPS + 1):
-                k = s - 1 if (rows and cache is not None) else None
-                if graphs is not None:
-                    graphs(text[:, :s], cached_positions=k)
-                else:
-                    model(vision, text[:, :s], kv_cache=cache, cached_positions=k)
+    def e_fn(t):
+        return embed[t]
 
-    with torch.no_grad():
-        cache = VisionKVCache(model, vision)
-    loop(cache)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 3
-    e0.record()
-    for _ in range(reps):
-        with torch.no_grad():
-            cache = VisionKVCache(model, vision)   # per-image K/V projection is part of a caption
-        loop(cache)
-    e1.record()
-    torch.cuda.synchronize()
-    ms_eager = e0.elapsed_time(e1) / reps
-    # uncached loop (what the reference does: re-project K/V every step)
-    e0.record()
-    loop(None)
-    e1.record()
-    torch.cuda.synchronize()
-    ms_uncached = e0.elapsed_time(e1)
-    # the same loop as one CUDA-graph replay per prefix length (graphs captured once per cache, i.e. per
-    # caption batch in a serving loop that keeps its buffers; capture time is not part of a caption)
-    from vlm_bridge_b200 import DecodeStepGraphs
-    ms_graph = None
-    try:
-        graphs = DecodeStepGraphs(model, cache)
-        loop(cache, graphs)
+    def l_fn(h):
+        return h[:, -1, :] @ head.t()
+
+    def timed(fn, reps=3):
+        fn()
         torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
-            loop(cache, graphs)
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        ms_graph = e0.elapsed_time(e1) / reps
+        return e0.elapsed_time(e1) / reps
+
+    # eager launches; a new cache per caption batch
+    ms_eager = timed(lambda: greedy_decode(model, vision, e_fn, l_fn, **kw))
+    # one CUDA graph of the bridge per prefix length, captured ONCE; every caption batch refills the cache in place
+    cache = VisionKVCache(model, vision)
+    graphs = DecodeStepGraphs(model, cache)
+    ms_graph, graph_err = None, None
+    try:
+        ms_graph = timed(lambda: greedy_decode(model, vision, e_fn, l_fn, kv_cache=cache, step_graphs=graphs,
+                                               refill_cache=True, **kw))
     except Exception as e:  # noqa: BLE001
         graph_err = repr(e)[:200]
-    ms = min(ms_eager, ms_graph) if ms_graph is not None else ms_eager
-    # K/V cache only (every text row of block 0's cross-attention recomputed every step), eager
-    loop(cache, rows=False)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(reps):
-        loop(cache, rows=False)
-    e1.record()
-    torch.cuda.synchronize()
-    ms_kv_only = e0.elapsed_time(e1) / reps
-    # kernel-level: cross-attention launches only
+    use_graphs = ms_graph is not None and ms_graph < ms_eager
+    ms = ms_graph if use_graphs else ms_eager
+
+    # end to end: image features from pinned host memory in, token ids to the host out, every caption batch
+    def e2e_once():
+        v = vision_h.to(dev, non_blocking=True)
+        if use_graphs:
+            ids, _ = greedy_decode(model, v, e_fn, l_fn, kv_cache=cache, step_graphs=graphs, refill_cache=True, **kw)
+        else:
+            ids, _ = greedy_decode(model, v, e_fn, l_fn, **kw)
+        ids_h.copy_(ids, non_blocking=True)
+        torch.cuda.synchronize()          # the caller needs the ids
+    ms_e2e = timed(e2e_once)
+    # variants (eager): no position rows; no cache at all (what the reference does: re-project K/V every step)
+    ms_kv_only = timed(lambda: greedy_decode(model, vision, e_fn, l_fn, cache_positions=False, **kw))
+    ms_uncached = timed(lambda: greedy_decode(model, vision, e_fn, l_fn, use_cache=False, **kw), reps=1)
+    # kernel-level: this library's launches of one caption batch (eager pass, events after every launch)
     _lib.profile_begin(torch.cuda.current_stream().cuda_stream)
-    loop(cache)
+    greedy_decode(model, vision, e_fn, l_fn, **kw)
     entries = _lib.profile_end()
-    # cross-attention launches over the cached K/V: the packed-layout decode kernel
-    cross_ms = sum(ms_ for name, ms_ in entries if name in ("attn_decode_packed", "attn_decode_tc"))
+    per_kernel: dict[str, float] = {}
+    for name, ms_ in entries:
+        per_kernel[name] = per_kernel.get(name, 0.0) + ms_
+    cross_ms = sum(v for k, v in per_kernel.items() if k in ("attn_decode_packed", "attn_decode_tc"))
+    gemm_ms = sum(v for k, v in per_kernel.items() if k.startswith("gemm_tcgen05"))
     bytes_total = sum(decode_bytes_per_step(DEC_B, s, N_VIS, position_rows=True) for s in range(1, DEC_STEPS + 1))
     achieved = bytes_total / (cross_ms * 1e-3) / 1e9 if cross_ms > 0 else 0.0
+    gflop = decode_gemm_flops(DEC_B, DEC_STEPS, N_VIS)
+    gemm_tf = gflop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "r01_ncu_decode_packed_summary.json")
     if os.path.exists(tp):
@@ -849,23 +963,32 @@ def bench_decode(model, dev, peaks, _lib) -> dict:
             traffic = json.load(f)["summary"]["dram_bytes_per_launch_len_q_1"]
         traffic_src = ("profiles/r01_ncu_decode_packed_summary.json: dram__bytes_read.sum + dram__bytes_write.sum of one "
                        "1-position launch (ncu --set full); algorithmic bytes of that launch: 76.1 MB")
+    tok = DEC_B * DEC_STEPS
     return {
-        "metric": "caption decode tokens/sec (bridge-only loop, cached vision K/V)",
-        "value": DEC_B * DEC_STEPS / (ms * 1e-3), "unit": "tokens/s", "ms_per_caption_batch": ms,
-        "ms_per_caption_batch_by_launch_mode": {"eager (incl. K/V projection + packing per caption batch)": ms_eager,
-                                                "graph replay per prefix length (cache and graphs reused)": ms_graph},
-        "uncached_tokens_per_s": DEC_B * DEC_STEPS / (ms_uncached * 1e-3),
-        "kv_cache_only_tokens_per_s": DEC_B * DEC_STEPS / (ms_kv_only * 1e-3),
+        "metric": "caption decode tokens/sec (greedy_decode: embed + bridge + read-out + argmax; cached vision K/V)",
+        "value": tok / (ms * 1e-3), "unit": "tokens/s", "ms_per_caption_batch": ms,
+        "launch_mode": "graph replay per prefix length, cache refilled in place per caption batch" if use_graphs else "eager launches",
+        "ms_per_caption_batch_by_launch_mode": {"eager (new VisionKVCache per caption batch)": ms_eager,
+                                                "graph replay (graphs captured once; K/V projection + packing refilled "
+                                                "in place per caption batch)": ms_graph, "graph_error": graph_err},
+        "e2e": {"value": tok / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_caption_batch": ms_e2e,
+                "h2d_bytes_per_step": vision_h.numel() * 4, "d2h_bytes_per_step": ids_h.numel() * 8,
+                "how": "per caption batch: image features H2D from pinned memory, greedy_decode, token ids D2H, host sync"},
+        "uncached_tokens_per_s": tok / (ms_uncached * 1e-3),
+        "kv_cache_only_tokens_per_s": tok / (ms_kv_only * 1e-3),
         "config": (f"C4: batch {DEC_B}, {DEC_STEPS} new tokens, Nv={N_VIS}; vision K/V cached per image, block 0's "
                    "cross-attention rows cached per text position, everything from block 0's non-causal "
-                   "self-attention on recomputed over the prefix every step"),
+                   f"self-attention on recomputed over the prefix every step; stand-in LM: embedding table + linear "
+                   f"read-out, vocabulary {V}"),
         "roofline": {"bound": "hbm", "kernel": "attn_decode_kernel<288, packed> for <= 32 positions (all 64 block-0 launches: 1 position each), attn_decode_tc_kernel<288> above (the 128 cross-attention launches)", "achieved": achieved,
                      "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": traffic,
                      "traffic_source": traffic_src, "algorithmic_bytes_total": bytes_total, "kernel_ms_total": cross_ms,
-                     "note": ("event-timed between eager launches. Graph-timed per launch (profiles/r01_exp_decode_v3.jsonl, "
-                              "r01_exp_decode_tc_v4.jsonl): 17-19 us (65-68 % of the HBM peak) up to 16 positions, 24-25 us up to 32 "
-                              "(legacy HMMA pipe), 28-31 us (47 %) for 33-64 on the tcgen05 kernel, whose M=64 MMAs cost >= 47 "
-                              "cycles each on the tensor pipe whatever their size")},
+                     "note": "event-timed between eager launches of one caption batch"},
+        "gemm_roofline": {"bound": "tensor", "kernel": "gemm_tcgen05 (prefix recompute: M = 32 * s rows)",
+                          "achieved": gemm_tf, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                          "frac": gemm_tf / peaks["bf16_burst"], "algorithmic_tflop_per_caption_batch": gflop / 1e12,
+                          "kernel_ms_total": gemm_ms},
+        "kernel_ms_per_caption_batch": {k: round(v, 4) for k, v in sorted(per_kernel.items())},
         "kv_cache_bytes": cache.nbytes,
     }
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200B_ABI_VERSION 2
+#define B200B_ABI_VERSION 3
 
 /* error codes (negative returns) */
 #define B200B_OK 0
@@ -343,6 +343,27 @@ int b200b_bridge_kv_backward(const b200b_bridge_dims* dims, const void* vision_b
                              size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------- *
+ * fp32 inference path (csrc/exact_fp32.cu). The reference decodes with no autocast: generate_caption
+ * runs the bridge in fp32 (full_model.py:221-261), and a greedy loop turns any logit perturbation
+ * larger than the top-2 margin into a different caption. These entry points compute the same block
+ * with fp32 operands, products and sums on the CUDA cores (FFMA GEMM accumulating K in index order,
+ * exact softmax, erf GELU), so that greedy token ids equal the fp32 reference's; the tensor-core
+ * entry points above reproduce the reference's training numerics (bf16 autocast) instead.
+ *
+ * `w` holds fp32 matrices here (the fp32 master weights in nn.Linear layout, no bf16 copy); kv is
+ * fp32 [Tv, nb*2D] with block i's K in columns [2iD, 2iD+D) and V in the next D. flags: only
+ * B200B_BRIDGE_PART_CROSS / PART_REST are honoured. No dropout (inference only), nothing is saved.
+ * ------------------------------------------------------------------------------------------- */
+size_t b200b_bridge_f32_workspace_bytes(const b200b_bridge_dims* dims);
+/* kv f32 [Tv, nb*2D] = vision f32 [Tv, Dv] @ wkv_all f32 [nb*2D, Dv]^T + bkv_all   (bridge_module.py:99-100) */
+int b200b_bridge_kv_project_f32(const b200b_bridge_dims* dims, const float* vision, const float* wkv_all,
+                                const float* bkv_all, float* kv, void* stream);
+/* x_out f32 [T, D] = BridgeBlock(x_in f32 [T, D], kv f32), eval mode   (bridge_module.py:300-335) */
+int b200b_bridge_block_forward_f32(const b200b_bridge_dims* dims, int block_index, const b200b_block_weights* w,
+                                   const float* x_in, const float* kv, float* x_out, void* workspace,
+                                   size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
  * Optimizer step over the flat arenas. Replaces GradScaler.unscale_, the
  * gradient-norm loop, clip_grad_norm_ and torch.optim.AdamW.step of the reference training step
  * (core_training_loop.py:84-104, training_setup.py:248-254) with two launches.
@@ -358,14 +379,18 @@ int b200b_bridge_kv_backward(const b200b_bridge_dims* dims, const void* vision_b
  * output of b200b_grad_sqnorm on the same gradients) they are clipped to max_grad_norm as
  * torch.nn.utils.clip_grad_norm_ does (max_grad_norm <= 0: no clipping) and the whole step is skipped
  * when the norm is not finite; it is also skipped when *found_inf != 0 (GradScaler). All scalars that
- * change every step and would otherwise need a host sync are read from device memory. */
+ * change every step and would otherwise need a host sync are read from device memory. With step_dev
+ * (device float[2], zero-initialised by the caller) the step count lives on the device as well:
+ * step_dev[0] = steps applied so far (the bias corrections use step_dev[0] + 1 and `step` is ignored),
+ * step_dev[1] = steps skipped; a one-thread kernel behind the update advances one of the two, so a
+ * skipped step does not advance the bias corrections (as torch's fused AdamW under GradScaler). */
 size_t b200b_grad_sqnorm_workspace_bytes(void);
 int b200b_grad_sqnorm(const float* grad, int64_t n, void* workspace, size_t workspace_bytes, float* out2,
                       void* stream);
 int b200b_adamw_fused(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* weights_bf16,
                       int64_t n, int64_t n_bf16, const float* sqnorm2, float max_grad_norm,
                       const float* grad_scale, const float* found_inf, float lr, float beta1, float beta2,
-                      float eps, float weight_decay, int64_t step, void* stream);
+                      float eps, float weight_decay, int64_t step, float* step_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------- *
  * Fused cross-entropy over the vocabulary logits. Replaces the label shift and

@@ -40,7 +40,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.b200b_abi_version() == 2
+    assert lib.b200b_abi_version() == 3
     lib.b200b_last_error.restype = ctypes.c_char_p
     assert isinstance(lib.b200b_last_error(), bytes)
 

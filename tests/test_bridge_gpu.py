@@ -217,3 +217,108 @@ def test_training_mode_dropout_is_unbiased_and_reproducible_in_backward():
     (g1,) = torch.autograd.grad(y.square().mean(), t, retain_graph=True)
     (g2,) = torch.autograd.grad(y.square().mean(), t)
     assert torch.equal(g1, g2)
+
+
+def test_dropout_statistics_at_real_widths():
+    """The d = 288 / d = 128 Philox paths at the real widths (1024 / 2304, heads 8 / 18, F = 9216): with p = 0.1
+    in train mode the mean over masks approaches the eval output, masks differ between calls, and the backward
+    regenerates the forward's masks (gradient from one forward computed twice is identical, and the gradient
+    averaged over masks approaches the eval gradient)."""
+    from vlm_bridge_b200 import BridgeLite
+
+    sd = O.init_state_dict(4)
+    cfg = dict(vision_dim=1024, language_dim=2304, num_blocks=2, num_heads_cross=8, num_heads_self=18)
+    m = BridgeLite(dropout=0.1, **cfg)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    g = torch.Generator().manual_seed(91)
+    vision = torch.randn(2, 257, 1024, generator=g).cuda()
+    text = torch.randn(2, 40, 2304, generator=g).cuda()
+    m.eval()
+    t0 = text.clone().requires_grad_()
+    y_eval = m(vision, t0)
+    (g_eval,) = torch.autograd.grad(y_eval.float().square().mean(), t0)
+    y_eval = y_eval.detach()
+    m.train()
+    n = 64
+    acc_y, acc_g, acc_y2 = torch.zeros_like(y_eval), torch.zeros_like(g_eval), torch.zeros_like(y_eval)
+    first = None
+    for i in range(n):
+        t = text.clone().requires_grad_()
+        y = m(vision, t)
+        (gt,) = torch.autograd.grad(y.float().square().mean(), t, retain_graph=(i == 0))
+        if i == 0:
+            (gt2,) = torch.autograd.grad(y.float().square().mean(), t)
+            assert torch.equal(gt, gt2)                # masks regenerated identically in the backward
+            first = y.detach().clone()
+        elif i == 1:
+            assert not torch.equal(first, y.detach())  # a new forward draws new masks
+        acc_y += y.detach(); acc_y2 += y.detach() ** 2; acc_g += gt
+    mean_y, mean_g = acc_y / n, acc_g / n
+    std_y = (acc_y2 / n - mean_y ** 2).clamp_min(0).sqrt()
+    # the mean of n masked outputs deviates from the eval output by ~ std / sqrt(n) plus the second-order
+    # effect of dropout inside the nonlinearities; 6 standard errors + 3 % of the output scale bounds both
+    bias = (mean_y - y_eval).abs()
+    assert float(std_y.mean()) > 1e-2 * float(y_eval.abs().mean())           # dropout really perturbs
+    assert bool((bias <= 6 * std_y / n ** 0.5 + 0.03 * y_eval.abs().max()).all())
+    assert float((mean_g - g_eval).norm() / g_eval.norm()) < 0.2
+
+
+def test_debug_forward_prints_reference_statistics(capsys):
+    """forward(..., debug=True) (bridge_module.py:427-454; called by every validation sample generation,
+    core_training_loop.py:317): same return value as debug=False, the reference's per-block lines, and the
+    NaN warning when a block output is not finite."""
+    cfg = dict(vision_dim=1024, language_dim=2304, num_blocks=2, num_heads_cross=8, num_heads_self=18)
+    sd = O.init_state_dict(6)
+    m = _make(cfg, sd).eval()
+    g = torch.Generator().manual_seed(66)
+    vision, text = torch.randn(2, 33, 1024, generator=g).cuda(), torch.randn(2, 9, 2304, generator=g).cuda()
+    with torch.no_grad():
+        y = m(vision, text)
+        capsys.readouterr()
+        y_dbg = m(vision, text, debug=True)
+    out = capsys.readouterr().out
+    assert torch.equal(y, y_dbg)
+    assert "Bridge Input - Vision: torch.Size([2, 33, 1024]), Text: torch.Size([2, 9, 2304])" in out
+    assert "Text stats: mean=" in out and "Vision stats: mean=" in out
+    assert "Block 1:" in out and "Block 2:" in out and "→" in out and "±" in out
+    assert "NaN" not in out and "Inf" not in out
+    # statistics printed for block 2 are those of the returned tensor
+    assert f"{float(y.mean()):.4f}±{float(y.std()):.4f}" in out
+    # autograd still works through the debug path (the reference's debug forward is an ordinary forward)
+    t = text.clone().requires_grad_()
+    yg = m(vision, t, debug=True)
+    yg.float().square().mean().backward()
+    assert t.grad is not None and torch.isfinite(t.grad).all()
+    capsys.readouterr()
+    bad = text.clone()
+    bad[0, 0, 0] = float("nan")
+    with torch.no_grad():
+        m(vision, bad, debug=True)
+    assert "NaN detected in Block 1 output" in capsys.readouterr().out
+
+
+def test_vision_features_requiring_grad_are_rejected():
+    cfg = dict(vision_dim=64, language_dim=128, num_blocks=2, num_heads_cross=2, num_heads_self=1)
+    from vlm_bridge_b200 import BridgeLite
+
+    m = BridgeLite(dropout=0.0, **cfg).cuda()
+    with pytest.raises(RuntimeError, match="vision_features must not require grad"):
+        m(torch.randn(1, 5, 64).cuda().requires_grad_(), torch.randn(1, 3, 128).cuda())
+
+
+def test_invalidate_weight_cache_after_data_writes():
+    """Writes through `.data` do not bump the version counter; `invalidate_weight_cache()` is the documented
+    remedy (INTEGRATION.md)."""
+    from vlm_bridge_b200 import BridgeLite
+
+    cfg = dict(vision_dim=64, language_dim=128, num_blocks=2, num_heads_cross=2, num_heads_self=1)
+    torch.manual_seed(1)
+    m = BridgeLite(dropout=0.0, **cfg).cuda().eval()
+    v, t = torch.randn(1, 5, 64).cuda(), torch.randn(1, 3, 128).cuda()
+    with torch.no_grad():
+        y0 = m(v, t)
+        m.bridge_blocks[1].ffn[3].weight.data.mul_(0.0)
+        m.invalidate_weight_cache()
+        y1 = m(v, t)
+    assert not torch.equal(y0, y1)

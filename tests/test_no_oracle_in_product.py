@@ -33,14 +33,18 @@ def test_package_has_no_cpu_or_eager_fallback():
 
 def test_bench_uses_oracle_only_in_cpu_legs():
     src = open(os.path.join(ROOT, "bench.py")).read()
+    # two imports, each inside its own helper: _cpu_oracle() (the port) and _cpu_reference_module() (the unmodified
+    # reference copied to oracle/_ref by oracle/make_ref.py); only the CPU legs (functions named cpu_*) call them
     uses = [m.start() for m in re.finditer(r"from oracle import", src)]
-    assert len(uses) == 1
-    # the single import sits inside _cpu_oracle(), which only the CPU legs (functions named cpu_*) call
-    head = src[:uses[0]]
-    assert head.rfind("def _cpu_oracle") == max(m.start() for m in re.finditer(r"^def \w+", head, flags=re.M))
-    for m in re.finditer(r"_cpu_oracle\(\)", src):
-        if src[m.start() - 4:m.start()] == "def ":
-            continue
-        enclosing = re.findall(r"^def (\w+)", src[:m.start()], flags=re.M)[-1]
-        assert enclosing.startswith("cpu_"), enclosing
+    assert len(uses) == 2
+    helpers = ("_cpu_oracle", "_cpu_reference_module")
+    for u in uses:
+        enclosing = re.findall(r"^def (\w+)", src[:u], flags=re.M)[-1]
+        assert enclosing in helpers, enclosing
+    for h in helpers:
+        for m in re.finditer(h + r"\(\)", src):
+            if src[m.start() - 4:m.start()] == "def ":
+                continue
+            enclosing = re.findall(r"^def (\w+)", src[:m.start()], flags=re.M)[-1]
+            assert enclosing.startswith("cpu_"), enclosing
     assert "/root/reference" not in src

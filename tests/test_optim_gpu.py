@@ -99,6 +99,22 @@ def test_nonfinite_gradients_skip_the_step():
     next(m.parameters()).grad[0, 0] = float("inf")
     opt.step()
     assert torch.equal(m._flat, before)
+    # a skipped step does not advance the step count (torch's fused AdamW under GradScaler behaves the same;
+    # the next step's bias corrections depend on it) and is counted as skipped
+    assert opt.skipped_steps == 1
+    assert float(opt.state_dict()["state"][0]["step"]) == 0.0
+    ref_params = [p.detach().clone().requires_grad_() for p in m.parameters()]
+    ref_opt = torch.optim.AdamW(ref_params, lr=1e-2, weight_decay=1e-2)
+    opt.zero_grad(set_to_none=True)
+    m(torch.randn(1, 3, 64).cuda(), torch.randn(1, 2, 128).cuda()).sum().backward()
+    for rp, p in zip(ref_params, m.parameters()):
+        rp.grad = p.grad.detach().clone()
+    torch.nn.utils.clip_grad_norm_(ref_params, 1.0)
+    ref_opt.step()
+    opt.step()
+    assert opt.skipped_steps == 1 and float(opt.state_dict()["state"][0]["step"]) == 1.0
+    for p, rp in zip(m.parameters(), ref_params):       # first applied step uses the step-1 bias corrections
+        assert _rel(p.detach(), rp.detach()) <= 2e-6
 
 
 def test_loss_trajectory_100_steps_matches_reference_numerics():

@@ -138,7 +138,7 @@ def _declare(lib) -> None:
     lib.b200b_grad_sqnorm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     lib.b200b_adamw_fused.restype = C.c_int
     lib.b200b_adamw_fused.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_int64, C.c_void_p, C.c_float, C.c_void_p,
-                                                          C.c_void_p] + [C.c_float] * 5 + [C.c_int64, C.c_void_p]
+                                                          C.c_void_p] + [C.c_float] * 5 + [C.c_int64, C.c_void_p, C.c_void_p]
     lib.b200b_cross_entropy_fwd.restype = C.c_int
     lib.b200b_cross_entropy_fwd.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p] + [C.c_int64] * 4 + [C.c_void_p] * 4
     lib.b200b_cross_entropy_bwd.restype = C.c_int

@@ -230,6 +230,13 @@ def _declare_bridge(lib) -> None:
     lib.b200b_bridge_kv_backward.restype = C.c_int
     lib.b200b_bridge_kv_backward.argtypes = [P(_BridgeDims), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.b200b_bridge_f32_workspace_bytes.restype = C.c_size_t
+    lib.b200b_bridge_f32_workspace_bytes.argtypes = [P(_BridgeDims)]
+    lib.b200b_bridge_kv_project_f32.restype = C.c_int
+    lib.b200b_bridge_kv_project_f32.argtypes = [P(_BridgeDims)] + [C.c_void_p] * 5
+    lib.b200b_bridge_block_forward_f32.restype = C.c_int
+    lib.b200b_bridge_block_forward_f32.argtypes = [P(_BridgeDims), C.c_int, P(_BlockPtrs), C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib._b200b_bridge_declared = True
 
 
@@ -404,9 +411,10 @@ class BridgeLite(nn.Module):
                            heads_self=self.num_heads_self, num_blocks=self.num_blocks, flags=flags)
 
     # -- vision K/V (shared with the decode cache) -------------------------------------------------
-    def project_vision_kv(self, vision_features: torch.Tensor):
+    def project_vision_kv(self, vision_features: torch.Tensor, out=None):
         """K/V of every block for `vision_features` [B, Nv, vision_dim] -> (vision_bf16, kv bf16
-        [B*Nv, num_blocks*2*language_dim]). Reference: bridge_module.py:99-100."""
+        [B*Nv, num_blocks*2*language_dim]). Reference: bridge_module.py:99-100. `out=(vision_bf16, kv)`
+        writes into existing tensors of those shapes."""
         self._ensure_flat()
         self._refresh_bf16()
         v = vision_features.detach().to(device=self._flat.device, dtype=torch.float32).contiguous()
@@ -415,31 +423,57 @@ class BridgeLite(nn.Module):
             raise RuntimeError(f"vision_features last dim {Dv} != vision_dim {self.vision_dim}")
         lay = self._layout
         D = self.language_dim
-        vb = torch.empty((B * Nv, Dv), device=v.device, dtype=torch.bfloat16)
-        kv = torch.empty((B * Nv, self.num_blocks * 2 * D), device=v.device, dtype=torch.bfloat16)
+        if out is not None:
+            vb, kv = out
+            if tuple(vb.shape) != (B * Nv, Dv) or tuple(kv.shape) != (B * Nv, self.num_blocks * 2 * D):
+                raise RuntimeError("project_vision_kv: out tensors have the wrong shape")
+        else:
+            vb = torch.empty((B * Nv, Dv), device=v.device, dtype=torch.bfloat16)
+            kv = torch.empty((B * Nv, self.num_blocks * 2 * D), device=v.device, dtype=torch.bfloat16)
         dims = self._dims(B, 1, Nv)
         _lib.check(_bridge_lib().b200b_bridge_kv_project(
             C.byref(dims), v.data_ptr(), self._w16.data_ptr() + 2 * lay.kv_w_start,
             self._flat.data_ptr() + 4 * lay.kv_b_start, vb.data_ptr(), kv.data_ptr(), _stream()), "kv_project")
         return vb, kv
 
-    def pack_vision_kv(self, kv: torch.Tensor, batch: int, len_vision: int) -> torch.Tensor:
+    def project_vision_kv_fp32(self, vision_features: torch.Tensor) -> torch.Tensor:
+        """fp32 K/V of every block, [B*Nv, num_blocks*2*language_dim], from the fp32 master weights: the
+        decode numerics of the reference, which runs generate_caption without autocast
+        (full_model.py:221-261 -> bridge_module.py:99-100)."""
+        self._ensure_flat()
+        v = vision_features.detach().to(device=self._flat.device, dtype=torch.float32).contiguous()
+        B, Nv, Dv = v.shape
+        if Dv != self.vision_dim:
+            raise RuntimeError(f"vision_features last dim {Dv} != vision_dim {self.vision_dim}")
+        lay = self._layout
+        kv = torch.empty((B * Nv, self.num_blocks * 2 * self.language_dim), device=v.device, dtype=torch.float32)
+        dims = self._dims(B, 1, Nv)
+        _lib.check(_bridge_lib().b200b_bridge_kv_project_f32(
+            C.byref(dims), v.data_ptr(), self._flat.data_ptr() + 4 * lay.kv_w_start,
+            self._flat.data_ptr() + 4 * lay.kv_b_start, kv.data_ptr(), _stream()), "kv_project_f32")
+        return kv
+
+    def pack_vision_kv(self, kv: torch.Tensor, batch: int, len_vision: int, out=None) -> torch.Tensor:
         """Decode layout of a `project_vision_kv` result: [B][blocks][heads][2][Nv][d+8] bf16 (flat uint8)."""
         lib = _bridge_lib()
         d = self.language_dim // self.num_heads_cross
         nbytes = lib.b200b_kv_cache_packed_bytes(batch, len_vision, self.num_heads_cross, d, self.num_blocks)
-        packed = torch.empty(nbytes, device=kv.device, dtype=torch.uint8)
+        packed = torch.empty(nbytes, device=kv.device, dtype=torch.uint8) if out is None else out
+        if packed.numel() != nbytes:
+            raise RuntimeError("pack_vision_kv: out has the wrong size")
         _lib.check(lib.b200b_kv_cache_pack(kv.data_ptr(), kv.stride(0), packed.data_ptr(), batch, len_vision,
                                            self.num_heads_cross, d, self.num_blocks, _stream()), "kv_cache_pack")
         return packed
 
-    def pack_vision_kv_tc(self, kv: torch.Tensor, batch: int, len_vision: int) -> torch.Tensor:
+    def pack_vision_kv_tc(self, kv: torch.Tensor, batch: int, len_vision: int, out=None) -> torch.Tensor:
         """tcgen05 decode layout of a `project_vision_kv` result (csrc/attention_tc.cu): per image / block /
         head, 32-key tiles stored as the swizzled shared-memory images the MMAs read."""
         lib = _bridge_lib()
         d = self.language_dim // self.num_heads_cross
         nbytes = lib.b200b_kv_cache_tc_bytes(batch, len_vision, self.num_heads_cross, d, self.num_blocks)
-        packed = torch.empty(nbytes, device=kv.device, dtype=torch.uint8)
+        packed = torch.empty(nbytes, device=kv.device, dtype=torch.uint8) if out is None else out
+        if packed.numel() != nbytes:
+            raise RuntimeError("pack_vision_kv_tc: out has the wrong size")
         _lib.check(lib.b200b_kv_cache_pack_tc(kv.data_ptr(), kv.stride(0), packed.data_ptr(), batch, len_vision,
                                               self.num_heads_cross, d, self.num_blocks, _stream()), "kv_cache_pack_tc")
         return packed
@@ -536,6 +570,61 @@ class BridgeLite(nn.Module):
                          flags=flags,
                          versions=self._w16_key)
         return out, state
+
+    def _run_forward_fp32(self, text: torch.Tensor, kv_cache, block_callback=None,
+                          cached_positions: Optional[int] = None) -> torch.Tensor:
+        """Inference forward with fp32 operands over an fp32 `VisionKVCache` (csrc/exact_fp32.cu): the
+        reference's decode numerics (no autocast, full_model.py:221-261). Same block / position-row
+        structure as `_run_forward`."""
+        self._ensure_flat()
+        dev = self._flat.device
+        if self.training and self.dropout_p > 0:
+            raise RuntimeError("the fp32 path is inference-only: call .eval() first")
+        if text.device != dev or text.dim() != 3 or text.shape[-1] != self.language_dim:
+            raise RuntimeError(f"text_embeddings must be a CUDA tensor [B, L, {self.language_dim}] on the module's device")
+        x = text.detach().to(torch.float32).contiguous()
+        B, L, D = x.shape
+        if kv_cache.batch != B:
+            raise RuntimeError("kv cache batch does not match text batch")
+        Nv = kv_cache.len_vision
+        lib = _bridge_lib()
+        dims = self._dims(B, L, Nv)
+        ws_bytes = lib.b200b_bridge_f32_workspace_bytes(C.byref(dims))
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        b32 = self._flat.data_ptr()
+        ptrs = self.__dict__.get("_ptrs32")
+        if ptrs is None or ptrs[0] != b32:
+            ptrs = (b32, [self._block_ptr_struct(0, b32, i, grads=False) for i in range(self.num_blocks)])
+            self.__dict__["_ptrs32"] = ptrs
+        ptrs = ptrs[1]
+        st = _stream()
+        kv = kv_cache.kv32
+        pos_cache = None
+        if cached_positions is not None:
+            pos_cache = kv_cache.position_rows(L, cached_positions, dev, D)
+        cur = x.view(B * L, D)
+        for i in range(self.num_blocks):
+            x_out = torch.empty((B * L, D), device=dev, dtype=torch.float32)
+            x_in, bdims = cur, dims
+            if i == 0 and pos_cache is not None:
+                k = int(cached_positions)
+                n_new = L - k
+                x_new = x[:, k:, :].contiguous()
+                cdims = self._dims(B, n_new, Nv, FLAG_PART_CROSS)
+                x1_new = torch.empty((B * n_new, D), device=dev, dtype=torch.float32)
+                _lib.check(lib.b200b_bridge_block_forward_f32(C.byref(cdims), 0, C.byref(ptrs[0]), x_new.data_ptr(),
+                                                              kv.data_ptr(), x1_new.data_ptr(), ws.data_ptr(), ws_bytes, st),
+                           "block_forward_f32(cross part)")
+                pos_cache[:, k:L].copy_(x1_new.view(B, n_new, D))
+                x_in = pos_cache[:, :L].contiguous().view(B * L, D)
+                bdims = self._dims(B, L, Nv, FLAG_PART_REST)
+            _lib.check(lib.b200b_bridge_block_forward_f32(C.byref(bdims), i, C.byref(ptrs[i]), x_in.data_ptr(),
+                                                          kv.data_ptr(), x_out.data_ptr(), ws.data_ptr(), ws_bytes, st),
+                       "block_forward_f32")
+            if block_callback is not None:
+                block_callback(i, cur.view(B, L, D), x_out.view(B, L, D))
+            cur = x_out
+        return cur.view(B, L, D)
 
     def _run_backward(self, state, d_out: torch.Tensor, text_needs_grad: bool):
         lay = self._layout
@@ -642,16 +731,30 @@ class BridgeLite(nn.Module):
         """
         params = [p for _, p in self._named_params()]
         needs_grad = torch.is_grad_enabled() and (text_embeddings.requires_grad or any(p.requires_grad for p in params))
+        if vision_features is not None and vision_features.requires_grad and torch.is_grad_enabled():
+            # the reference's vision encoder runs under no_grad (vision_encoder.py:89); this module has no
+            # data-gradient kernel for the K/V projection and would silently hand back None
+            raise RuntimeError("vision_features must not require grad: the bridge treats the image features as "
+                               "constants (no gradient flows to the vision encoder)")
         if debug:
             return self._forward_debug(vision_features, text_embeddings, kv_cache)
+        fp32 = kv_cache is not None and getattr(kv_cache, "precision", "bf16") == "fp32"
         if needs_grad:
             if kv_cache is not None or cached_positions is not None:
                 raise RuntimeError("kv_cache is inference-only (use torch.no_grad())")
-            out = _BridgeFunction.apply(self, vision_features, text_embeddings, *params)
-        else:
-            out, _ = self._run_forward(vision_features, text_embeddings, keep_for_backward=False, kv_cache=kv_cache,
-                                       cached_positions=cached_positions)
-        return out if text_embeddings.dtype == torch.float32 else out
+            return _BridgeFunction.apply(self, vision_features, text_embeddings, *params)
+        if fp32:
+            return self._run_forward_fp32(text_embeddings, kv_cache, cached_positions=cached_positions)
+        out, _ = self._run_forward(vision_features, text_embeddings, keep_for_backward=False, kv_cache=kv_cache,
+                                   cached_positions=cached_positions)
+        return out      # fp32 like the reference's residual stream under autocast
+
+    def invalidate_weight_cache(self) -> None:
+        """Force the bf16 operand copies to be re-made on the next call. The copies are refreshed when a
+        parameter's version counter changes, which in-place autograd-visible updates (optimizers,
+        `p.add_()`, `load_state_dict`) bump; writes through `p.data` (`p.data.copy_()`, EMA swaps, a custom
+        broadcast, an external kernel writing the flat buffer) do not -- call this after any of those."""
+        self._w16_key = None
 
     def _forward_debug(self, vision_features, text_embeddings, kv_cache):
         """debug=True: print the reference's per-block statistics (bridge_module.py:427-454).
@@ -677,6 +780,8 @@ class BridgeLite(nn.Module):
                 self._run_forward(vision_features, text_embeddings, False, kv_cache, block_callback=cb)
                 self.train(was)
             return _BridgeFunction.apply(self, vision_features, text_embeddings, *params)
+        if kv_cache is not None and getattr(kv_cache, "precision", "bf16") == "fp32":
+            return self._run_forward_fp32(text_embeddings, kv_cache, block_callback=cb)
         out, _ = self._run_forward(vision_features, text_embeddings, False, kv_cache, block_callback=cb)
         return out
 

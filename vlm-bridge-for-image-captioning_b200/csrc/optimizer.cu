@@ -72,6 +72,7 @@ struct AdamParams {
   const float* grad_scale; // device scalar the gradients were multiplied by (GradScaler), or null
   const float* found_inf;  // device scalar != 0 -> skip the step (GradScaler), or null
   float max_norm, lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2_sqrt;
+  const float* step_dev;   // {steps applied so far, steps skipped}: when given, the bias corrections come from it
 };
 
 __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v, const AdamParams& a, float gmul) {
@@ -84,7 +85,24 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
   return p;
 }
 
-__global__ void __launch_bounds__(256) adamw_fused_kernel(const AdamParams a) {
+__device__ __forceinline__ bool adam_skipped(const AdamParams& a) {
+  if (a.found_inf != nullptr && __ldg(a.found_inf) != 0.f) return true;
+  return a.sqnorm != nullptr && __ldg(a.sqnorm + 1) != 0.f;   // non-finite gradients
+}
+
+// after the update: count the step as applied or skipped (torch's fused / capturable AdamW does not advance
+// `step` on a step GradScaler skips; the next step's bias corrections depend on it)
+__global__ void adamw_count_kernel(const AdamParams a, float* step_dev) {
+  if (adam_skipped(a)) step_dev[1] += 1.0f;
+  else step_dev[0] += 1.0f;
+}
+
+__global__ void __launch_bounds__(256) adamw_fused_kernel(AdamParams a) {
+  if (a.step_dev != nullptr) {
+    const double t = (double)__ldg(a.step_dev) + 1.0;
+    a.bias_corr1 = (float)(1.0 - pow((double)a.beta1, t));
+    a.bias_corr2_sqrt = (float)sqrt(1.0 - pow((double)a.beta2, t));
+  }
   float gmul = 1.0f;
   if (a.grad_scale != nullptr) gmul = 1.0f / __ldg(a.grad_scale);
   if (a.found_inf != nullptr && __ldg(a.found_inf) != 0.f) return;
@@ -146,11 +164,11 @@ extern "C" int b200b_grad_sqnorm(const float* grad, int64_t n, void* workspace, 
 extern "C" int b200b_adamw_fused(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* weights_bf16,
                                  int64_t n, int64_t n_bf16, const float* sqnorm2, float max_grad_norm,
                                  const float* grad_scale, const float* found_inf, float lr, float beta1, float beta2,
-                                 float eps, float weight_decay, int64_t step, void* stream_) {
+                                 float eps, float weight_decay, int64_t step, float* step_dev, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || (n % 4) || n_bf16 < 0 || n_bf16 > n || (n_bf16 % 4) ||
-      step < 1) {
-    set_last_error("adamw_fused: null pointer, n / n_bf16 not multiples of 4, or step < 1");
+      (step < 1 && step_dev == nullptr)) {
+    set_last_error("adamw_fused: null pointer, n / n_bf16 not multiples of 4, or step < 1 without step_dev");
     return B200B_ERR_ARG;
   }
   const uintptr_t al = reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
@@ -175,10 +193,15 @@ extern "C" int b200b_adamw_fused(float* param, const float* grad, float* exp_avg
   a.found_inf = found_inf;
   a.max_norm = max_grad_norm;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
-  a.bias_corr1 = (float)(1.0 - pow((double)beta1, (double)step));
-  a.bias_corr2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  a.step_dev = step_dev;
+  const double t = step < 1 ? 1.0 : (double)step;
+  a.bias_corr1 = (float)(1.0 - pow((double)beta1, t));
+  a.bias_corr2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
   long long blocks = (a.n4 + 255) / 256;
   if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
   adamw_fused_kernel<<<(int)blocks, 256, 0, stream>>>(a);
-  return check_launch("adamw_fused", stream);
+  rc = check_launch("adamw_fused", stream);
+  if (rc != B200B_OK || step_dev == nullptr) return rc;
+  adamw_count_kernel<<<1, 1, 0, stream>>>(a, step_dev);
+  return check_launch("adamw_count", stream);
 }

@@ -81,21 +81,37 @@ def greedy_decode(bridge, vision_features: torch.Tensor, embed_fn: Callable[[tor
                   eos_token_id: Optional[int] = None, max_new_tokens: int = 50,
                   kv_cache: Optional[VisionKVCache] = None, use_cache: bool = True,
                   step_graphs: Optional[DecodeStepGraphs] = None, use_graphs: bool = False,
-                  cache_positions: bool = True):
+                  cache_positions: bool = True, precision: str = "bf16", refill_cache: bool = False):
     """Returns (ids [B, 1 + max_new_tokens] int64 incl. BOS, lengths [B] int64): row b's caption is
     ids[b, 1:lengths[b]] (EOS excluded); positions from lengths[b] on are what the lock-step loop kept
     generating and are to be ignored. `use_graphs` replays one captured CUDA graph of the bridge per
     prefix length (`DecodeStepGraphs`; pass `step_graphs` to reuse graphs captured for the same cache).
     `cache_positions` keeps block 0's cross-attention rows per text position in the cache (valid because
     `embed_fn` is a per-token lookup: the prefix rows do not change when a token is appended); pass
-    False for an `embed_fn` that mixes positions."""
+    False for an `embed_fn` that mixes positions.
+
+    `precision="fp32"` runs the bridge with fp32 operands (csrc/exact_fp32.cu): the reference's own decode
+    numerics (generate_caption runs without autocast, full_model.py:221-261), for which the token ids equal
+    the fp32 reference's on every step; "bf16" is the tensor-core path (the reference's autocast numerics).
+    `refill_cache=True` with a `kv_cache` from an earlier call recomputes that cache in place for
+    `vision_features` (same shape), so `step_graphs` captured over it are replayed for new images."""
     was_training = bridge.training
     bridge.eval()
     try:
         B = vision_features.shape[0]
         dev = vision_features.device
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if precision == "fp32" and not use_cache:
+            raise RuntimeError("precision='fp32' reads an fp32 VisionKVCache: use_cache must stay True")
         if use_cache and kv_cache is None:
-            kv_cache = VisionKVCache(bridge, vision_features)
+            kv_cache = VisionKVCache(bridge, vision_features, precision=precision,
+                                     max_positions=max(64, max_new_tokens))
+        elif use_cache:
+            if kv_cache.precision != precision:
+                raise RuntimeError(f"kv_cache holds {kv_cache.precision} K/V but precision={precision!r} was asked for")
+            if refill_cache:
+                kv_cache.refill(vision_features)
         if (use_graphs or step_graphs is not None) and use_cache:
             if step_graphs is None or step_graphs.cache is not kv_cache:
                 step_graphs = DecodeStepGraphs(bridge, kv_cache)
@@ -116,9 +132,10 @@ def greedy_decode(bridge, vision_features: torch.Tensor, embed_fn: Callable[[tor
                 logits = logits[:, -1, :]
             logits = logits.float()
             # numerical guards of the reference, as tensor ops (no host sync)
-            bad = torch.isnan(logits).any()
+            # (per row: the reference applies them to one caption at a time, full_model.py:270-283)
+            bad = torch.isnan(logits).any(dim=-1, keepdim=True)
             logits = torch.where(bad, torch.zeros_like(logits), logits)
-            logits = torch.where(torch.isinf(logits).any(), logits.clamp(min=-100, max=100), logits)
+            logits = torch.where(torch.isinf(logits).any(dim=-1, keepdim=True), logits.clamp(min=-100, max=100), logits)
             ids[:, step + 1] = torch.argmax(logits, dim=-1)
         if eos_token_id is None:
             lengths = torch.full((B,), 1 + max_new_tokens, dtype=torch.long, device=dev)

@@ -50,7 +50,9 @@ class BridgeAdamW(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self.max_grad_norm = max_grad_norm
         self.last_grad_norm: Optional[torch.Tensor] = None
-        self._steps = 0
+        self._steps = 0                  # host view of the step count (exact once `_sync_steps` has run)
+        self._step_dev = None            # device float[2] = {steps applied, steps skipped}: the authoritative count
+        self._steps_dirty = False
         self.gather_steps = 0
         self._m = self._v = self._ws = self._norm2 = self._gflat = None
 
@@ -68,6 +70,8 @@ class BridgeAdamW(torch.optim.Optimizer):
         nbytes = _lib.lib().b200b_grad_sqnorm_workspace_bytes()
         self._ws = torch.zeros(nbytes, dtype=torch.uint8, device=flat.device)
         self._norm2 = torch.zeros(2, dtype=torch.float32, device=flat.device)
+        skipped = 0.0 if self._step_dev is None else float(self._step_dev[1].item())
+        self._step_dev = torch.zeros(2, dtype=torch.float32, device=flat.device)
         for name, p in b._named_params():
             o = lay.offsets[name]
             m = self._m[o:o + p.numel()].view(p.shape)
@@ -83,6 +87,21 @@ class BridgeAdamW(torch.optim.Optimizer):
         if len(steps) > 1:
             raise RuntimeError("BridgeAdamW needs one common step count for all parameters")
         self._steps = steps.pop() if steps else 0
+        self._step_dev.copy_(torch.tensor([float(self._steps), skipped]))
+        self._steps_dirty = False
+
+    def _sync_steps(self) -> None:
+        """Read the device-side step count back (one host sync; only where a host value is needed:
+        state_dict(), `skipped_steps`). A step that GradScaler or a non-finite gradient norm skipped has not
+        advanced it -- the behaviour of torch's fused AdamW, which the bias corrections depend on."""
+        if self._steps_dirty and self._step_dev is not None:
+            self._steps = int(self._step_dev[0].item())
+            self._steps_dirty = False
+
+    @property
+    def skipped_steps(self) -> int:
+        """Steps that were not applied (found_inf from GradScaler, or a non-finite gradient norm). Syncs."""
+        return 0 if self._step_dev is None else int(self._step_dev[1].item())
 
     def load_state_dict(self, state_dict) -> None:
         super().load_state_dict(state_dict)
@@ -91,8 +110,10 @@ class BridgeAdamW(torch.optim.Optimizer):
         if ps and ps[0] in self.state:
             s = self.state[ps[0]]["step"]
             self._steps = int(s.item() if torch.is_tensor(s) else s)
+            self._steps_dirty = False
 
     def state_dict(self):
+        self._sync_steps()
         for st in self.state.values():
             if "step" in st:
                 st["step"] = torch.tensor(float(self._steps))
@@ -140,14 +161,14 @@ class BridgeAdamW(torch.optim.Optimizer):
         found_inf = getattr(self, "found_inf", None)
         _lib.check(lib.b200b_grad_sqnorm(g.data_ptr(), lay.total, self._ws.data_ptr(), self._ws.numel(),
                                          self._norm2.data_ptr(), st), "grad_sqnorm")
-        self._steps += 1
+        self._steps_dirty = True      # the device counter advances only if the kernel applies the update
         lr = group["lr"]
         _lib.check(lib.b200b_adamw_fused(
             b._flat.data_ptr(), g.data_ptr(), self._m.data_ptr(), self._v.data_ptr(), b._w16.data_ptr(), lay.total,
             lay.n_weights, self._norm2.data_ptr(), float(self.max_grad_norm or 0.0),
             None if grad_scale is None else grad_scale.data_ptr(), None if found_inf is None else found_inf.data_ptr(),
             float(lr.item() if torch.is_tensor(lr) else lr), group["betas"][0], group["betas"][1], group["eps"],
-            group["weight_decay"], self._steps, st), "adamw_fused")
+            group["weight_decay"], 0, self._step_dev.data_ptr(), st), "adamw_fused")
         inv = 1.0 if grad_scale is None else 1.0 / grad_scale
         self.last_grad_norm = self._norm2[0].sqrt() * inv
         # the parameters changed in place behind torch's back: bump their version counters (stale K/V
