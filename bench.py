@@ -307,7 +307,8 @@ def run_b200_arm(args) -> int:
         enable_data_parallel(model, grad_dtype=torch.float32 if args.grad_dtype == "f32" else torch.bfloat16,
                              backend=args.dp_backend, nvls_blocks=args.nvls_blocks, nvls_threads=args.nvls_threads,
                              bucket_bytes=args.bucket_mb << 20, exclusive_sms=args.nvls_exclusive,
-                             fp32_multicast=args.nvls_fp32_multicast)
+                             fp32_multicast=args.nvls_fp32_multicast, nvls_unroll=args.nvls_unroll,
+                             materialize_fp32=not args.dp_bf16_arena)
         model._bucket_hook.diag_skip_convert = args.diag_dp_skip_convert
 
     def step(v, t):
@@ -530,6 +531,7 @@ def run_b200_arm(args) -> int:
         # NCCL in fp32); got = what every rank's .grad holds after a step with the exchange on, launched
         # eagerly and as a replay of a freshly captured graph
         def flat_grads():
+            model.materialize_grads()          # no-op unless the exchange left the weight gradients in the bf16 arena
             return torch.cat([p.grad.detach().reshape(-1).float() for p in params])
 
         model.eval()
@@ -1032,6 +1034,10 @@ def main() -> int:
     ap.add_argument("--nvls-blocks", type=int, default=32)
     ap.add_argument("--nvls-threads", type=int, default=512)
     ap.add_argument("--nvls-exclusive", action="store_true", help="reserve --nvls-blocks SMs for the exchange")
+    ap.add_argument("--nvls-unroll", type=int, default=4, choices=[4, 8, 16], help="16-byte units in flight per thread")
+    ap.add_argument("--dp-bf16-arena", action="store_true",
+                    help="leave the averaged weight gradients in the bf16 arena (no bf16 -> fp32 pass; what BridgeAdamW "
+                         "consumes); default materialises fp32 .grad every step")
     ap.add_argument("--nvls-fp32-multicast", action="store_true", help="broadcast fp32 into .grad (no conversion pass)")
     ap.add_argument("--diag-dp-skip-convert", action="store_true",
                     help="diagnostics: skip the bf16 -> fp32 pass of the exchange (gradients are then incomplete)")

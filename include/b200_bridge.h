@@ -195,6 +195,12 @@ typedef struct b200b_attn_args {
 } b200b_attn_args;
 
 int b200b_attention_fwd(const b200b_attn_args* args, void* stream);
+/* Which implementation b200b_attention_fwd / _bwd use for query blocks longer than 64 rows or with dropout
+ * (the training shapes): bit 0 = forward, bit 1 = backward on the tcgen05 tensor cores (csrc/attention_train_tc.cu:
+ * TMA-fed 64-byte-swizzle tiles, S / O / dQ accumulators in tensor memory, P as a tensor-memory operand); a
+ * cleared bit keeps the mma.sync kernels of csrc/attention.cu. Default 3 (environment B200B_ATTN_TC overrides).
+ * Returns the previous mask; mask < 0 only queries. Process-wide; meant for A/B measurements and tests. */
+int b200b_attention_set_tc(int mask);
 size_t b200b_attention_bwd_workspace_bytes(int batch, int heads, int len_q, int len_k);
 int b200b_attention_bwd(const b200b_attn_args* args, void* stream);
 
@@ -383,11 +389,16 @@ int b200b_bridge_block_forward_f32(const b200b_bridge_dims* dims, int block_inde
  * (device float[2], zero-initialised by the caller) the step count lives on the device as well:
  * step_dev[0] = steps applied so far (the bias corrections use step_dev[0] + 1 and `step` is ignored),
  * step_dev[1] = steps skipped; a one-thread kernel behind the update advances one of the two, so a
- * skipped step does not advance the bias corrections (as torch's fused AdamW under GradScaler). */
+ * skipped step does not advance the bias corrections (as torch's fused AdamW under GradScaler).
+ * grad_bf16 (both functions; may be NULL): the gradients of the first n_bf16 elements -- the 2-D weights -- are
+ * read from this bf16 array instead of `grad` (same element offsets). That is the averaged bf16 weight-gradient
+ * arena of the data-parallel exchange: the optimizer consumes it directly and the exchange needs no
+ * bf16 -> fp32 pass over 158 M elements (0.95 GB of HBM traffic per step next to the backward GEMMs). */
 size_t b200b_grad_sqnorm_workspace_bytes(void);
-int b200b_grad_sqnorm(const float* grad, int64_t n, void* workspace, size_t workspace_bytes, float* out2,
-                      void* stream);
-int b200b_adamw_fused(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* weights_bf16,
+int b200b_grad_sqnorm(const float* grad, int64_t n, const void* grad_bf16, int64_t n_bf16, void* workspace,
+                      size_t workspace_bytes, float* out2, void* stream);
+int b200b_adamw_fused(float* param, const float* grad, const void* grad_bf16, float* exp_avg, float* exp_avg_sq,
+                      void* weights_bf16,
                       int64_t n, int64_t n_bf16, const float* sqnorm2, float max_grad_norm,
                       const float* grad_scale, const float* found_inf, float lr, float beta1, float beta2,
                       float eps, float weight_decay, int64_t step, float* step_dev, void* stream);
@@ -438,7 +449,11 @@ int b200b_bf16_to_f32(const void* in_bf16, float* out, int64_t n, float scale, v
  * one call at a time per communicator. The collective number is `epoch` (1, 2, 3, ...), or, with
  * epoch_base != NULL, `epoch + *epoch_base` read on the device when the kernel runs: a captured CUDA
  * graph then numbers its collectives 1..n and advances *epoch_base by n once per replay.
- * A rank that never arrives makes the others trap after ~10 s instead of hanging.
+ * A rank that never arrives within comm->timeout_s seconds (default 600, the order of a process-group timeout:
+ * ranks legitimately skew by seconds around checkpoint writes, validation or first-step initialisation) makes
+ * the others give the collective up: with comm->error_word (a host-visible, e.g. pinned, uint32 the caller
+ * zero-initialises) they store a non-zero code there -- 1 + the rank waited for, phase << 8, block << 12 -- and
+ * return, so the caller can raise an ordinary error; without it they trap.
  * ------------------------------------------------------------------------------------------- */
 #define B200B_NVLS_MAX_RANKS 8
 #define B200B_NVLS_MAX_BLOCKS 160
@@ -449,6 +464,9 @@ typedef struct b200b_nvls_comm {
   void* local_base;                     /* this rank's own copy */
   void* flags[B200B_NVLS_MAX_RANKS];    /* flag array of rank q as mapped in this process */
   int32_t rank, world;
+  int32_t timeout_s;                    /* barrier wait limit in seconds; <= 0: 600 */
+  int32_t reserved;
+  void* error_word;                     /* host-visible uint32 receiving a code on timeout, or NULL (trap) */
 } b200b_nvls_comm;
 /* flags of b200b_allreduce_nvls */
 /* out_f32 is the MULTICAST address of a second symmetric buffer (same offset on every rank, e.g. the
@@ -459,6 +477,9 @@ typedef struct b200b_nvls_comm {
  * so no compute CTA is co-resident with the exchange; `blocks` must be even. Use together with
  * b200b_set_sm_limit(SMs - blocks) on the compute side. */
 #define B200B_NVLS_EXCLUSIVE_SMS 2u
+/* bits 8..15 of flags: 16-byte units each thread keeps in flight (0 = 4; 4, 8 or 16). The exchange is bound by
+ * bytes in flight (a multimem.ld_reduce round trip is ~5 us), so small grids need the deeper setting. */
+#define B200B_NVLS_UNROLL(n) (((uint32_t)(n) & 0xffu) << 8)
 size_t b200b_allreduce_nvls_flag_bytes(void);
 int b200b_allreduce_nvls(const b200b_nvls_comm* comm, int dtype, int64_t byte_offset, int64_t bytes,
                          float scale, float* out_f32, uint32_t epoch, const uint32_t* epoch_base,

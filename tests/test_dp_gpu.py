@@ -46,6 +46,9 @@ def _worker(rank, world, port, out):
         for p in m.parameters():
             p.grad = None
         m(v, t).float().square().mean().backward()
+        if m._grad16 is not None:              # materialize_fp32=False: the 2-D weights carry no .grad yet
+            assert all(p.grad is None for p in m.parameters() if p.dim() == 2)
+            m.materialize_grads()
         return torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone()
 
     with torch.no_grad():
@@ -59,7 +62,11 @@ def _worker(rank, world, port, out):
             # fp32 multicast straight into .grad, and the exchange on 4 SMs of its own (CTA pairs)
             ("nvls_bf16_mc32", "nvls", torch.bfloat16, 1.5e-2, dict(fp32_multicast=True)),
             ("nvls_bf16_excl", "nvls", torch.bfloat16, 1.5e-2,
-             dict(fp32_multicast=True, exclusive_sms=True, nvls_blocks=4, nvls_threads=1024))):
+             dict(fp32_multicast=True, exclusive_sms=True, nvls_blocks=4, nvls_threads=1024)),
+            # deeper per-thread pipelining; averaged gradients left in the bf16 arena and materialised on demand
+            ("nvls_bf16_u16", "nvls", torch.bfloat16, 1.5e-2, dict(nvls_unroll=16, nvls_blocks=8, nvls_threads=1024)),
+            ("nvls_bf16_lazy", "nvls", torch.bfloat16, 1.5e-2, dict(nvls_unroll=8, materialize_fp32=False)),
+            ("nccl_bf16_lazy", "nccl", torch.bfloat16, 1.5e-2, dict(materialize_fp32=False))):
         red = enable_data_parallel(m, bucket_bytes=8 << 20, grad_dtype=dtype, backend=backend, **kw)
         got = grads(*shard(rank))
         torch.cuda.synchronize()

@@ -58,7 +58,8 @@ class ColsumTask(C.Structure):
 
 class NvlsComm(C.Structure):
     _fields_ = [("multicast_base", C.c_void_p), ("local_base", C.c_void_p), ("flags", C.c_void_p * 8),
-                ("rank", C.c_int32), ("world", C.c_int32)]
+                ("rank", C.c_int32), ("world", C.c_int32), ("timeout_s", C.c_int32), ("reserved", C.c_int32),
+                ("error_word", C.c_void_p)]
 
 
 class AttnArgs(C.Structure):
@@ -135,15 +136,17 @@ def _declare(lib) -> None:
     lib.b200b_grad_sqnorm_workspace_bytes.restype = C.c_size_t
     lib.b200b_grad_sqnorm_workspace_bytes.argtypes = []
     lib.b200b_grad_sqnorm.restype = C.c_int
-    lib.b200b_grad_sqnorm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.b200b_grad_sqnorm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     lib.b200b_adamw_fused.restype = C.c_int
-    lib.b200b_adamw_fused.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_int64, C.c_void_p, C.c_float, C.c_void_p,
+    lib.b200b_adamw_fused.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_int64, C.c_void_p, C.c_float, C.c_void_p,
                                                           C.c_void_p] + [C.c_float] * 5 + [C.c_int64, C.c_void_p, C.c_void_p]
     lib.b200b_cross_entropy_fwd.restype = C.c_int
     lib.b200b_cross_entropy_fwd.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p] + [C.c_int64] * 4 + [C.c_void_p] * 4
     lib.b200b_cross_entropy_bwd.restype = C.c_int
     lib.b200b_cross_entropy_bwd.argtypes = ([C.c_void_p, C.c_int, C.c_int64, C.c_void_p] + [C.c_int64] * 4 +
                                             [C.c_void_p] * 4 + [C.c_int64, C.c_void_p])
+    lib.b200b_attention_set_tc.restype = C.c_int
+    lib.b200b_attention_set_tc.argtypes = [C.c_int]
     lib.b200b_set_sm_limit.restype = None
     lib.b200b_set_sm_limit.argtypes = [C.c_int]
     lib.b200b_get_sm_limit.restype = C.c_int

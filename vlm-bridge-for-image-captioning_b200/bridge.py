@@ -298,6 +298,7 @@ class BridgeLite(nn.Module):
         # data-parallel reducer (parallel.GradBucketReducer) driven by _run_backward
         self._bucket_hook = None
         self._last_grad_arena: Optional[torch.Tensor] = None
+        self._grad16: Optional[torch.Tensor] = None      # averaged bf16 weight gradients not yet materialised as .grad
         self._graph_recast = True
 
     # -- init exactly as the reference (bridge_module.py:394-404) ---------------------------------
@@ -707,10 +708,14 @@ class BridgeLite(nn.Module):
             reducer.vectors_ready(lay.kv_b_start, lay.block_v_start[0])
             reducer.finish()
         self._last_grad_arena = garena
+        # data parallel with `materialize_fp32=False`: the averaged weight gradients stay in the bf16 arena (read by
+        # BridgeAdamW directly); the weights get no `.grad` until materialize_grads() is called
+        lazy16 = reducer is not None and wgrad_bf16 and not reducer.materialize_fp32
+        self._grad16 = g16 if lazy16 else None
         grads = []
         for name, p in self._named_params():
-            if p.requires_grad:
-                o = lay.offsets[name]
+            o = lay.offsets[name]
+            if p.requires_grad and not (lazy16 and o < lay.n_weights):
                 grads.append(garena[o:o + p.numel()].view(p.shape))
             else:
                 grads.append(None)
@@ -748,6 +753,22 @@ class BridgeLite(nn.Module):
         out, _ = self._run_forward(vision_features, text_embeddings, keep_for_backward=False, kv_cache=kv_cache,
                                    cached_positions=cached_positions)
         return out      # fp32 like the reference's residual stream under autocast
+
+    def materialize_grads(self) -> None:
+        """Data parallel with `enable_data_parallel(..., materialize_fp32=False)`: turn the averaged bf16
+        weight-gradient arena of the last backward into ordinary fp32 `.grad` tensors (one HBM-bound pass).
+        `BridgeAdamW` does not need this; a loop that inspects or clips `.grad` itself does."""
+        g16 = self.__dict__.get("_grad16")
+        if g16 is None:
+            return
+        lay, garena = self._layout, self._last_grad_arena
+        _lib.check(_lib.lib().b200b_bf16_to_f32(g16.data_ptr(), garena.data_ptr(), lay.n_weights, 1.0, _stream()),
+                   "bf16_to_f32(materialize_grads)")
+        for name, p in self._named_params():
+            o = lay.offsets[name]
+            if p.requires_grad and o < lay.n_weights:
+                p.grad = garena[o:o + p.numel()].view(p.shape)
+        self._grad16 = None
 
     def invalidate_weight_cache(self) -> None:
         """Force the bf16 operand copies to be re-made on the next call. The copies are refreshed when a

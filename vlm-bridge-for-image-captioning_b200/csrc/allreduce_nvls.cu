@@ -43,7 +43,9 @@
 namespace b200b {
 
 constexpr int kNvlsMaxThreads = 1024;
-constexpr int kNvlsUnroll = 4;  // 16-byte units in flight per thread
+// 16-byte units in flight per thread: 4 (default), 8 or 16, chosen by the caller (bits 8..15 of `flags`). A
+// multimem.ld_reduce round trip through the switch takes ~5 us, so the exchange is bound by bytes in flight:
+// 32 CTAs x 512 threads x 4 units = 1 MB gives ~200 GB/s; fewer, fatter CTAs need the deeper unroll.
 
 struct NvlsParams {
   uint64_t mc;                           // multicast address of the first unit of the bucket
@@ -57,6 +59,8 @@ struct NvlsParams {
   uint32_t epoch;                        // collective number (added to *epoch_base when that is given)
   const uint32_t* epoch_base;            // device counter advanced by the caller once per step, or nullptr
   int rank, world;
+  long long timeout_cycles;              // barrier wait limit in SM clock cycles
+  uint32_t* error_word;                  // host-visible word that receives a code when the wait expires, or nullptr
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -81,7 +85,16 @@ __device__ __forceinline__ void barrier_blocks(const NvlsParams& p, uint32_t epo
     const uint32_t* mine = p.flags[p.rank] + slot + q;
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
-      if (clock64() - t0 > 20000000000LL) {  // ~10 s: a rank never arrived; fail loudly, do not hang
+      if (clock64() - t0 > p.timeout_cycles) {
+        // a rank never arrived within the limit (default: minutes, like a process-group timeout). With an error
+        // word the failure is reported to the host, which raises at its next look (parallel.py), and this
+        // collective is abandoned -- its output is garbage, but the CUDA context survives; without one, trap.
+        if (p.error_word != nullptr) {
+          // code: 1 + waiting-for rank | phase << 8 | block << 12
+          const uint32_t code = (uint32_t)(q + 1) | ((uint32_t)phase << 8) | ((uint32_t)blockIdx.x << 12);
+          asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.error_word), "r"(code) : "memory");
+          break;
+        }
         printf("b200b: nvls all-reduce barrier timed out (rank %d block %d phase %d waiting for rank %d)\n", p.rank,
                (int)blockIdx.x, phase, q);
         __trap();
@@ -131,7 +144,7 @@ __device__ __forceinline__ uint4 scale_unit(uint4 v, float s) {
   return v;
 }
 
-template <bool BF16>
+template <bool BF16, int kNvlsUnroll>
 __global__ void __launch_bounds__(kNvlsMaxThreads) allreduce_nvls_kernel(const NvlsParams p) {
   const uint32_t epoch = p.epoch + (p.epoch_base != nullptr ? __ldcg(p.epoch_base) : 0u);
   barrier_blocks(p, epoch, 0);
@@ -287,8 +300,30 @@ extern "C" int b200b_allreduce_nvls(const b200b_nvls_comm* comm, int dtype, int6
   p.world = comm->world;
   p.mc_out = out_mc ? reinterpret_cast<uint64_t>(out_f32) : 0;
   if (out_mc) p.out_f32 = nullptr;
-  void (*kern)(const NvlsParams) = out_mc ? allreduce_nvls_bcast32_kernel
-                                   : (dtype == B200B_DTYPE_BF16 ? allreduce_nvls_kernel<true> : allreduce_nvls_kernel<false>);
+  const int unroll = (int)((flags >> 8) & 0xffu);
+  if (unroll != 0 && unroll != 4 && unroll != 8 && unroll != 16) {
+    set_last_error("allreduce_nvls: units in flight per thread (flags bits 8..15) must be 0 (= 4), 4, 8 or 16");
+    return B200B_ERR_ARG;
+  }
+  void (*kern)(const NvlsParams);
+  if (out_mc) kern = allreduce_nvls_bcast32_kernel;
+  else if (dtype == B200B_DTYPE_BF16)
+    kern = unroll == 16 ? allreduce_nvls_kernel<true, 16> : (unroll == 8 ? allreduce_nvls_kernel<true, 8> : allreduce_nvls_kernel<true, 4>);
+  else
+    kern = unroll == 16 ? allreduce_nvls_kernel<false, 16> : (unroll == 8 ? allreduce_nvls_kernel<false, 8> : allreduce_nvls_kernel<false, 4>);
+  {
+    // wait limit of the cross-rank barriers: comm->timeout_s seconds (<= 0: 600 s), converted with the SM clock
+    static int khz = 0;
+    if (khz == 0) {
+      int dev = 0, v = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, dev);
+      khz = v > 0 ? v : 1965000;
+    }
+    const long long secs = comm->timeout_s > 0 ? comm->timeout_s : 600;
+    p.timeout_cycles = secs * (long long)khz * 1000LL;
+    p.error_word = reinterpret_cast<uint32_t*>(comm->error_word);
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)blocks);
@@ -298,8 +333,9 @@ extern "C" int b200b_allreduce_nvls(const b200b_nvls_comm* comm, int dtype, int6
   if (exclusive) {
     // claim the SM: no CTA that needs more than the few KB left can become co-resident
     constexpr int kHogBytes = 200 * 1024;
-    static bool attr_done[3] = {false, false, false};
-    const int ki = out_mc ? 0 : (dtype == B200B_DTYPE_BF16 ? 1 : 2);
+    static bool attr_done[7] = {false, false, false, false, false, false, false};
+    const int ui = unroll == 16 ? 2 : (unroll == 8 ? 1 : 0);
+    const int ki = out_mc ? 0 : (dtype == B200B_DTYPE_BF16 ? 1 + ui : 4 + ui);
     if (!attr_done[ki]) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kHogBytes);
       if (e != cudaSuccess) {

@@ -930,6 +930,9 @@ static int validate_common(const b200b_attn_args* a, const char* what) {
   return B200B_OK;
 }
 
+// attention_train_tc.cu: the tcgen05 forward; *taken = 1 when it launched (or failed), 0 when the shape is not its
+int attention_fwd_tc(const b200b_attn_args* a, cudaStream_t stream, int* taken);
+
 static AttnParams make_params(const b200b_attn_args* a) {
   AttnParams p;
   memset(&p, 0, sizeof(p));
@@ -962,6 +965,11 @@ extern "C" int b200b_attention_fwd(const b200b_attn_args* a, void* stream_) {
       case 128: return launch_decode<128, false>(p, stream);
       default: return launch_decode<288, false>(p, stream);
     }
+  }
+  {
+    int taken = 0;
+    rc = attention_fwd_tc(a, stream, &taken);
+    if (taken) return rc;
   }
   switch (a->head_dim) {
     case 64: return launch_fwd<64>(p, stream);

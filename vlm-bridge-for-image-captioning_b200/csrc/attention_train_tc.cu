@@ -1,0 +1,357 @@
+// Training attention on the 5th-generation tensor cores (tcgen05.mma, accumulators in tensor memory).
+//
+// Replaces F.scaled_dot_product_attention in the training forward (bridge_module.py:132-139: cross-attention,
+// 8 heads of 288 over 257 / 1370 vision tokens; :230-237: non-causal, unmasked self-attention, 18 heads of 128),
+// including the head split / merge views (:103-115, :201-213). The mma.sync kernels of attention.cu (which top
+// out near 144 TF/s on B200's legacy tensor pipe) stay as the path for query blocks this kernel does not cover
+// and as an A/B switch (B200B_ATTN_TC=0).
+//
+// One CTA per (128 query rows, head, image):
+//   warp 5   TMA producer: the Q block once, then K and V tiles of 64 keys through two 2-deep rings, every tile
+//            fetched as HD/32 boxes of [rows][32 columns] with the 64-byte swizzle (tensor maps over the
+//            projection outputs, so the per-head column slice is read in place; rows past the sequence end
+//            arrive as zeros)
+//   warp 4   one elected thread issues the MMAs: S = Q K^T (M = 128, N = 64, K = HD; both operands K-major from
+//            shared memory) into one of two S buffers in tensor memory, and O += P V (A = P read from TENSOR
+//            memory, B = the V tile as an MN-major shared-memory operand -- V is stored [key][d], d contiguous;
+//            N = HD is issued as 160 + 128 columns for HD = 288)
+//   warps 0-3  one thread per query row (M = 128: TMEM lane = row): tcgen05.ld of the S row, online softmax in the
+//            exp2 domain with a lazily updated reference maximum (O in tensor memory is only rescaled when a row
+//            maximum grows by more than 2^8), dropout on the probabilities (Philox mask, same element indexing as
+//            the backward kernels), P packed to bf16 and stored back into tensor memory as the A operand of the
+//            P V product (it never touches shared memory); at the end O / l as bf16 to global memory and the
+//            row's log-sum-exp for the backward.
+// Operand layouts and descriptor forms were measured with tests/gpu_checks/probe_umma_layouts.cu
+// (profiles/r02_probe_umma_layouts.jsonl): 64-byte-swizzle K-major tiles for any K that is a multiple of 16,
+// MN-major tiles for K extents of 64 / 128 rows, A from tensor memory.
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/b200_bridge.h"
+#include "common.cuh"
+#include "launch.h"
+
+namespace b200b {
+
+struct FwdTcParams {
+  __nv_bfloat16* o; long long ldo;
+  float* lse2;                       // [B, H, Lq], log2 domain
+  int B, H, Lq, Lk, Lkp;
+  float scale_log2;
+  DropoutCfg drop;
+  uint32_t drop_stream;
+};
+
+constexpr int kFBM = 128;            // query rows per CTA
+constexpr int kFBN = 64;             // keys per tile
+constexpr int kFThreads = 192;
+
+template <int HD>
+struct FwdTcCfg {
+  static constexpr int kChunks = HD / 32;                 // 32-column (64-byte) chunks per row
+  static constexpr int kQBytes = kFBM * HD * 2;
+  static constexpr int kTileBytes = kFBN * HD * 2;        // one K or V tile
+  static constexpr int kN0 = HD > 256 ? 160 : HD;         // P V issued as kN0 (+ kN1) output columns
+  static constexpr int kN1 = HD - kN0;
+  static constexpr int kSCol = 0;                         // TMEM: S buffers [0, 128)
+  static constexpr int kPCol = 2 * kFBN;                  //       P buffers [128, 192) (bf16 pairs: 32 columns each)
+  static constexpr int kOCol = kPCol + kFBN;              //       O [192, 192 + HD)
+  static constexpr uint32_t kTmemCols = (kOCol + HD) <= 256 ? 256 : 512;
+  static constexpr size_t kSmemBytes = (size_t)kQBytes + 4 * (size_t)kTileBytes + 1024;
+  static_assert(HD % 32 == 0 && kN0 % 32 == 0 && kN1 % 32 == 0 && kN0 <= 256 && kOCol + HD <= 512, "head dim");
+};
+
+template <int HD>
+__global__ void __launch_bounds__(kFThreads, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_v, const FwdTcParams p) {
+  using Cfg = FwdTcCfg<HD>;
+  extern __shared__ uint8_t smem_ftc_raw[];
+  // q_full: Q landed; k_full / v_full: a tile landed; k_free / v_free: the MMAs that read it completed;
+  // s_full: S(t) produced; p_full: P(t) stored (S(t) read, O rescaled if needed); pv_done: P V(t) completed
+  __shared__ __align__(8) uint64_t q_full, k_full[2], k_free[2], v_full[2], v_free[2], s_full[2], p_full[2], pv_done[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kFBM, h = blockIdx.y, b = blockIdx.z;
+  const uint32_t s0 = (smem_u32(smem_ftc_raw) + 1023u) & ~1023u;
+  const uint32_t q_tile = s0;
+  const uint32_t k_tile0 = s0 + Cfg::kQBytes;
+  const uint32_t v_tile0 = k_tile0 + 2 * Cfg::kTileBytes;
+  const int nt = (p.Lk + kFBN - 1) / kFBN;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&q_full, 1);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_free[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_free[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_smem, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  if (warp == 5 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  pdl_launch_dependents();
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 5) {
+    // ------------------------------------ TMA producer ------------------------------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&q_full, Cfg::kQBytes);
+#pragma unroll
+      for (int c = 0; c < Cfg::kChunks; ++c)
+        tma_load_4d(q_tile + (uint32_t)c * kFBM * 64, &tm_q, smem_u32(&q_full), c * 32, h, q0, b);
+      for (int t = 0; t < nt; ++t) {
+        const int st = t & 1;
+        if (t >= 2) mbar_wait(&k_free[st], (uint32_t)(((t >> 1) - 1) & 1));
+        mbar_arrive_expect_tx(&k_full[st], Cfg::kTileBytes);
+#pragma unroll
+        for (int c = 0; c < Cfg::kChunks; ++c)
+          tma_load_4d(k_tile0 + (uint32_t)st * Cfg::kTileBytes + (uint32_t)c * kFBN * 64, &tm_k, smem_u32(&k_full[st]),
+                      c * 32, h, t * kFBN, b);
+        if (t >= 2) mbar_wait(&v_free[st], (uint32_t)(((t >> 1) - 1) & 1));
+        mbar_arrive_expect_tx(&v_full[st], Cfg::kTileBytes);
+#pragma unroll
+        for (int c = 0; c < Cfg::kChunks; ++c)
+          tma_load_4d(v_tile0 + (uint32_t)st * Cfg::kTileBytes + (uint32_t)c * kFBN * 64, &tm_v, smem_u32(&v_full[st]),
+                      c * 32, h, t * kFBN, b);
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------ MMA issue ------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(kFBM, kFBN, false, false);
+      constexpr uint32_t idesc_o0 = umma_idesc_bf16(kFBM, Cfg::kN0, false, true);
+      constexpr uint32_t idesc_o1 = umma_idesc_bf16(kFBM, Cfg::kN1 > 0 ? Cfg::kN1 : 16, false, true);
+      auto issue_s = [&](int t) {
+        const int st = t & 1;
+        mbar_wait(&k_full[st], (uint32_t)((t >> 1) & 1));
+        tc_fence_after();
+        const uint32_t kt = k_tile0 + (uint32_t)st * Cfg::kTileBytes;
+        const uint32_t d = tmem_base + (uint32_t)(Cfg::kSCol + st * kFBN);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          umma_bf16(d, desc_sw64_kmajor(q_tile, kFBM, ks), desc_sw64_kmajor(kt, kFBN, ks), idesc_s, ks > 0);
+        umma_commit(&s_full[st]);
+        umma_commit(&k_free[st]);
+      };
+      mbar_wait(&q_full, 0);
+      issue_s(0);
+      if (nt > 1) issue_s(1);
+      for (int t = 0; t < nt; ++t) {
+        const int st = t & 1;
+        mbar_wait(&p_full[st], (uint32_t)((t >> 1) & 1));
+        mbar_wait(&v_full[st], (uint32_t)((t >> 1) & 1));
+        tc_fence_after();
+        const uint32_t vt = v_tile0 + (uint32_t)st * Cfg::kTileBytes;
+        const uint32_t pa = tmem_base + (uint32_t)(Cfg::kPCol + st * (kFBN / 2));
+        const uint32_t od = tmem_base + (uint32_t)Cfg::kOCol;
+#pragma unroll
+        for (int kc = 0; kc < kFBN / 16; ++kc) {
+          umma_bf16_tmem_a(od, pa + (uint32_t)(kc * 8), desc_sw64_mnmajor(vt, kFBN, 0, kc), idesc_o0, (t | kc) != 0);
+          if constexpr (Cfg::kN1 > 0)
+            umma_bf16_tmem_a(od + (uint32_t)Cfg::kN0, pa + (uint32_t)(kc * 8),
+                             desc_sw64_mnmajor(vt, kFBN, Cfg::kN0 / 32, kc), idesc_o1, (t | kc) != 0);
+        }
+        umma_commit(&pv_done[st]);
+        umma_commit(&v_free[st]);
+        // S(t + 2) overwrites the S buffer whose row the softmax warps finished reading before p_full(t)
+        if (t + 2 < nt) issue_s(t + 2);
+      }
+    }
+  } else {
+    // ------------------------------------ softmax: one thread per query row ------------------------------------
+    const DropoutCfg drop = dropout_resolve(p.drop);
+    const int row = warp * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const size_t bh = (size_t)b * p.H + h;
+    const uint64_t ridx = (bh * p.Lq + (uint64_t)(q0 + row)) * (uint64_t)p.Lkp;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int t = 0; t < nt; ++t) {
+      const int st = t & 1;
+      mbar_wait(&s_full[st], (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+      float sv[kFBN];
+      float tmax = -INFINITY;
+      {
+        uint32_t v[kFBN / 16][16];
+#pragma unroll
+        for (int g = 0; g < kFBN / 16; ++g)
+          tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kSCol + st * kFBN + g * 16), v[g]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < kFBN / 16; ++g)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x = (t * kFBN + g * 16 + j < p.Lk) ? __uint_as_float(v[g][j]) * p.scale_log2 : -INFINITY;
+            sv[g * 16 + j] = x;
+            tmax = fmaxf(tmax, x);
+          }
+      }
+      float alpha = 1.0f;
+      if (tmax > m_run + 8.0f) {
+        alpha = exp2f(m_run - tmax);   // 0 on the first tile
+        m_run = tmax;
+      }
+      float rs = 0.f;
+#pragma unroll
+      for (int j = 0; j < kFBN; ++j) {
+        sv[j] = exp2f(sv[j] - m_run);
+        rs += sv[j];
+      }
+      l_run = l_run * alpha + rs;
+      if (drop.thr != 0) {
+#pragma unroll
+        for (int j8 = 0; j8 < kFBN / 8; ++j8) {
+          const uint4 bits = dropout_bits8(drop, p.drop_stream, (ridx + (uint64_t)(t * kFBN + j8 * 8)) >> 3);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) sv[j8 * 8 + e] = dropout_keep(bits, e, drop.thr) ? sv[j8 * 8 + e] * drop.scale : 0.f;
+        }
+      }
+      // P buffer st was last read by P V(t - 2)
+      if (t >= 2) mbar_wait(&pv_done[st], (uint32_t)(((t >> 1) - 1) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int g = 0; g < kFBN / 32; ++g) {
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = pack_bf16(sv[g * 32 + 2 * j], sv[g * 32 + 2 * j + 1]);
+        tmem_st_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kPCol + st * (kFBN / 2) + g * 16), w);
+      }
+      if (t >= 1) {
+        const unsigned moved = __ballot_sync(0xffffffffu, alpha != 1.0f);
+        if (moved) {   // rare: a row maximum of this warp jumped; rescale its 32 rows of O once P V(t - 1) is in
+          mbar_wait(&pv_done[(t - 1) & 1], (uint32_t)(((t - 1) >> 1) & 1));
+          tc_fence_after();
+#pragma unroll 1
+          for (int c0 = 0; c0 < HD; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kOCol + c0), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+            tmem_st_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kOCol + c0), v);
+          }
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[st]);
+    }
+    mbar_wait(&pv_done[(nt - 1) & 1], (uint32_t)(((nt - 1) >> 1) & 1));
+    tc_fence_after();
+    const bool valid = q0 + row < p.Lq;
+    const float inv = 1.0f / l_run;
+    if (valid) p.lse2[bh * p.Lq + q0 + row] = m_run + log2f(l_run);
+    __nv_bfloat16* dst = p.o + ((size_t)b * p.Lq + (valid ? q0 + row : 0)) * p.ldo + (size_t)h * HD;
+#pragma unroll 1
+    for (int c0 = 0; c0 < HD; c0 += 32) {
+      uint32_t v0[16], v1[16];
+      tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kOCol + c0), v0);
+      tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kOCol + c0 + 16), v1);
+      tmem_ld_wait();
+      if (valid) {
+        uint4 u[4];
+        uint32_t* w = reinterpret_cast<uint32_t*>(u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          w[j] = pack_bf16(__uint_as_float(v0[2 * j]) * inv, __uint_as_float(v0[2 * j + 1]) * inv);
+          w[8 + j] = pack_bf16(__uint_as_float(v1[2 * j]) * inv, __uint_as_float(v1[2 * j + 1]) * inv);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + c0 + j * 8) = u[j];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <int HD>
+static int launch_fwd_tc(const b200b_attn_args* a, cudaStream_t stream) {
+  using Cfg = FwdTcCfg<HD>;
+  static bool attr_done = false;   // idempotent; a race only repeats the call
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_last_error("attention_fwd (tcgen05): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_done = true;
+  }
+  CUtensorMap tq, tk, tv;
+  int rc = make_tmap_heads_sw64(&tq, a->q, a->ldq, HD, a->heads, a->len_q, a->batch, kFBM);
+  if (rc != B200B_OK) return rc;
+  rc = make_tmap_heads_sw64(&tk, a->k, a->ldk, HD, a->heads, a->len_k, a->batch, kFBN);
+  if (rc != B200B_OK) return rc;
+  rc = make_tmap_heads_sw64(&tv, a->v, a->ldv, HD, a->heads, a->len_k, a->batch, kFBN);
+  if (rc != B200B_OK) return rc;
+  FwdTcParams p;
+  p.o = reinterpret_cast<__nv_bfloat16*>(a->o);
+  p.ldo = a->ldo;
+  p.lse2 = a->lse;
+  p.B = a->batch; p.H = a->heads; p.Lq = a->len_q; p.Lk = a->len_k; p.Lkp = (a->len_k + 7) & ~7;
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
+  p.drop_stream = a->dropout_stream;
+  p.drop = make_dropout_cfg(a->dropout_p, a->seed, &p.drop_stream);
+  dim3 grid((a->len_q + kFBM - 1) / kFBM, a->heads, a->batch);
+  launch_pdl(kPdlAttn, attn_fwd_tc_kernel<HD>, grid, dim3(kFThreads), Cfg::kSmemBytes, stream, tq, tk, tv, p);
+  return check_launch("attn_fwd_tc", stream);
+}
+
+// bit 0 = tcgen05 forward, bit 1 = tcgen05 backward where they apply (default 3); the environment variable
+// B200B_ATTN_TC sets the initial value, b200b_attention_set_tc() changes it (A/B measurements, tests)
+static int g_attn_tc = -1;
+int attn_tc_mask() {
+  if (g_attn_tc < 0) {
+    const char* e = getenv("B200B_ATTN_TC");
+    g_attn_tc = e ? atoi(e) : 3;
+  }
+  return g_attn_tc;
+}
+
+// Forward through the tcgen05 kernel when the shape qualifies; returns 1 if it was not taken (caller falls back).
+int attention_fwd_tc(const b200b_attn_args* a, cudaStream_t stream, int* taken) {
+  *taken = 0;
+  if (!(attn_tc_mask() & 1)) return B200B_OK;
+  // tensor maps need 16-byte aligned bases and row pitches; the head slices must tile into 32-column boxes
+  const uintptr_t al = reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) | reinterpret_cast<uintptr_t>(a->v) |
+                       reinterpret_cast<uintptr_t>(a->o);
+  if ((al & 15) || (a->ldq % 8) || (a->ldk % 8) || (a->ldv % 8) || (a->ldo % 8)) return B200B_OK;
+  int rc;
+  switch (a->head_dim) {
+    case 64: rc = launch_fwd_tc<64>(a, stream); break;
+    case 128: rc = launch_fwd_tc<128>(a, stream); break;
+    case 288: rc = launch_fwd_tc<288>(a, stream); break;
+    default: return B200B_OK;
+  }
+  *taken = 1;
+  return rc;
+}
+
+}  // namespace b200b
+
+extern "C" int b200b_attention_set_tc(int mask) {
+  const int prev = b200b::attn_tc_mask();
+  if (mask >= 0) b200b::g_attn_tc = mask;
+  return prev;
+}

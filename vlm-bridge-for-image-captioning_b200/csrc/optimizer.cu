@@ -30,7 +30,10 @@ __device__ __forceinline__ float block_sum(float v, float* red /*[8]*/) {
 
 // out[0] = sum g^2 (fixed summation order: per-thread strided, block tree, then the partials in block
 // order by the last block to finish), out[1] = 1 if that sum is not finite. `state` = {ticket counter}.
+// The first n4_bf16 groups of four are read from g16 (bf16: the averaged weight-gradient arena of the
+// data-parallel exchange) when it is given, everything else from g (fp32, same element offsets).
 __global__ void __launch_bounds__(kNormThreads) grad_sqnorm_kernel(const float4* __restrict__ g, long long n4,
+                                                                   const uint2* __restrict__ g16, long long n4_bf16,
                                                                    float* __restrict__ partials,
                                                                    unsigned int* __restrict__ ticket,
                                                                    float* __restrict__ out) {
@@ -38,7 +41,13 @@ __global__ void __launch_bounds__(kNormThreads) grad_sqnorm_kernel(const float4*
   __shared__ bool last;
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 v = __ldg(g + i);
+    float4 v;
+    if (i < n4_bf16) {
+      const uint2 h = __ldg(g16 + i);
+      v = make_float4(bf16_lo(h.x), bf16_hi(h.x), bf16_lo(h.y), bf16_hi(h.y));
+    } else {
+      v = __ldg(g + i);
+    }
     s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
   s = block_sum(s, red);
@@ -64,6 +73,7 @@ __global__ void __launch_bounds__(kNormThreads) grad_sqnorm_kernel(const float4*
 struct AdamParams {
   float4* p;
   const float4* g;
+  const uint2* g16;        // bf16 gradients of the first n4_bf16 groups (data-parallel bf16 arena), or null
   float4* m;
   float4* v;
   uint2* w16;              // bf16 mirror of the first n4_bf16 float4 groups (may be null)
@@ -116,7 +126,13 @@ __global__ void __launch_bounds__(256) adamw_fused_kernel(AdamParams a) {
   }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n4; i += (long long)gridDim.x * blockDim.x) {
     float4 p = a.p[i], m = a.m[i], v = a.v[i];
-    const float4 g = __ldg(a.g + i);
+    float4 g;
+    if (a.g16 != nullptr && i < a.n4_bf16) {
+      const uint2 h = __ldg(a.g16 + i);
+      g = make_float4(bf16_lo(h.x), bf16_hi(h.x), bf16_lo(h.y), bf16_hi(h.y));
+    } else {
+      g = __ldg(a.g + i);
+    }
     adam_one(p.x, g.x, m.x, v.x, a, gmul);
     adam_one(p.y, g.y, m.y, v.y, a, gmul);
     adam_one(p.z, g.z, m.z, v.z, a, gmul);
@@ -134,12 +150,17 @@ using namespace b200b;
 
 extern "C" size_t b200b_grad_sqnorm_workspace_bytes(void) { return (size_t)(148 * 8 + 64) * sizeof(float); }
 
-extern "C" int b200b_grad_sqnorm(const float* grad, int64_t n, void* workspace, size_t workspace_bytes, float* out2,
-                                 void* stream_) {
+extern "C" int b200b_grad_sqnorm(const float* grad, int64_t n, const void* grad_bf16, int64_t n_bf16, void* workspace,
+                                 size_t workspace_bytes, float* out2, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!grad || !workspace || !out2 || n <= 0 || (n % 4) || (reinterpret_cast<uintptr_t>(grad) & 15) ||
       (reinterpret_cast<uintptr_t>(workspace) & 15)) {
     set_last_error("grad_sqnorm: need 16-byte aligned pointers and n a positive multiple of 4");
+    return B200B_ERR_ARG;
+  }
+  if (grad_bf16 == nullptr) n_bf16 = 0;
+  if (n_bf16 < 0 || n_bf16 > n || (n_bf16 % 4) || (reinterpret_cast<uintptr_t>(grad_bf16) & 7)) {
+    set_last_error("grad_sqnorm: the bf16 part needs 0 <= n_bf16 <= n, n_bf16 %% 4 == 0 and an 8-byte aligned pointer");
     return B200B_ERR_ARG;
   }
   if (workspace_bytes < b200b_grad_sqnorm_workspace_bytes()) {
@@ -156,12 +177,14 @@ extern "C" int b200b_grad_sqnorm(const float* grad, int64_t n, void* workspace, 
   // workspace: [0] ticket counter (zero before the first use: the caller zero-fills once), then partials
   unsigned int* ticket = reinterpret_cast<unsigned int*>(workspace);
   float* partials = reinterpret_cast<float*>(workspace) + 16;
-  grad_sqnorm_kernel<<<(int)blocks, kNormThreads, 0, stream>>>(reinterpret_cast<const float4*>(grad), n4, partials, ticket,
-                                                              out2);
+  grad_sqnorm_kernel<<<(int)blocks, kNormThreads, 0, stream>>>(reinterpret_cast<const float4*>(grad), n4,
+                                                              reinterpret_cast<const uint2*>(grad_bf16), n_bf16 / 4,
+                                                              partials, ticket, out2);
   return check_launch("grad_sqnorm", stream);
 }
 
-extern "C" int b200b_adamw_fused(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* weights_bf16,
+extern "C" int b200b_adamw_fused(float* param, const float* grad, const void* grad_bf16, float* exp_avg, float* exp_avg_sq,
+                                 void* weights_bf16,
                                  int64_t n, int64_t n_bf16, const float* sqnorm2, float max_grad_norm,
                                  const float* grad_scale, const float* found_inf, float lr, float beta1, float beta2,
                                  float eps, float weight_decay, int64_t step, float* step_dev, void* stream_) {
@@ -173,7 +196,8 @@ extern "C" int b200b_adamw_fused(float* param, const float* grad, float* exp_avg
   }
   const uintptr_t al = reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
                        reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq);
-  if ((al & 15) || (n_bf16 > 0 && (weights_bf16 == nullptr || (reinterpret_cast<uintptr_t>(weights_bf16) & 7)))) {
+  if ((al & 15) || (reinterpret_cast<uintptr_t>(grad_bf16) & 7) ||
+      (n_bf16 > 0 && (weights_bf16 == nullptr || (reinterpret_cast<uintptr_t>(weights_bf16) & 7)))) {
     set_last_error("adamw_fused: arenas must be 16-byte aligned (bf16 mirror 8-byte)");
     return B200B_ERR_ALIGN;
   }
@@ -183,6 +207,7 @@ extern "C" int b200b_adamw_fused(float* param, const float* grad, float* exp_avg
   AdamParams a;
   a.p = reinterpret_cast<float4*>(param);
   a.g = reinterpret_cast<const float4*>(grad);
+  a.g16 = reinterpret_cast<const uint2*>(grad_bf16);
   a.m = reinterpret_cast<float4*>(exp_avg);
   a.v = reinterpret_cast<float4*>(exp_avg_sq);
   a.w16 = reinterpret_cast<uint2*>(weights_bf16);

@@ -119,21 +119,30 @@ class BridgeAdamW(torch.optim.Optimizer):
                 st["step"] = torch.tensor(float(self._steps))
         return super().state_dict()
 
-    def _flat_grads(self) -> torch.Tensor:
-        """The gradients as one flat fp32 tensor in arena order: the bridge's own gradient arena when
-        every `.grad` is still the view autograd installed (the normal case), else a gathered copy."""
+    def _flat_grads(self):
+        """(flat fp32 gradients in arena order, bf16 weight-gradient arena or None). The bridge's own gradient
+        arena when every `.grad` is still the view autograd installed (the normal case), else a gathered copy.
+        Data parallel with `materialize_fp32=False`: the 2-D weights have no `.grad`; their averaged gradients
+        are the bf16 arena the exchange left behind, which the kernels read in place of the fp32 values."""
         b = self.bridge
         lay = b._layout
         named = b._named_params()
+        arena = b._last_grad_arena
+        g16 = b.__dict__.get("_grad16")
+        if g16 is not None and arena is not None:
+            base = arena.data_ptr()
+            if all((lay.offsets[n] < lay.n_weights and p.grad is None) or
+                   (p.grad is not None and p.grad.data_ptr() == base + 4 * lay.offsets[n]) for n, p in named):
+                return arena, g16
+            b.materialize_grads()       # someone replaced a .grad: fall back to ordinary fp32 gradients
         g0 = named[0][1].grad
         if g0 is None:
             raise RuntimeError("BridgeAdamW.step(): parameters have no gradients")
         base = g0.data_ptr() - 4 * lay.offsets[named[0][0]]
-        arena = b._last_grad_arena
         if arena is not None and arena.data_ptr() == base and all(
                 p.grad is not None and p.grad.dtype == torch.float32 and p.grad.data_ptr() == base + 4 * lay.offsets[n]
                 for n, p in named):
-            return arena
+            return arena, None
         self.gather_steps += 1          # diagnostics: steps that could not use the arena in place
         if self._gflat is None or self._gflat.device != g0.device:
             self._gflat = torch.empty(lay.total, device=g0.device, dtype=torch.float32)
@@ -142,7 +151,7 @@ class BridgeAdamW(torch.optim.Optimizer):
                 raise RuntimeError(f"BridgeAdamW.step(): {n} has no gradient")
             o = lay.offsets[n]
             self._gflat[o:o + p.numel()].view(p.shape).copy_(p.grad)
-        return self._gflat
+        return self._gflat, None
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -154,17 +163,18 @@ class BridgeAdamW(torch.optim.Optimizer):
         b = self.bridge
         lay = b._layout
         group = self.param_groups[0]
-        g = self._flat_grads()
+        g, g16 = self._flat_grads()
+        g16_ptr = None if g16 is None else g16.data_ptr()
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         lib = _lib.lib()
         grad_scale = getattr(self, "grad_scale", None)     # set by GradScaler.step for the duration of this call
         found_inf = getattr(self, "found_inf", None)
-        _lib.check(lib.b200b_grad_sqnorm(g.data_ptr(), lay.total, self._ws.data_ptr(), self._ws.numel(),
-                                         self._norm2.data_ptr(), st), "grad_sqnorm")
+        _lib.check(lib.b200b_grad_sqnorm(g.data_ptr(), lay.total, g16_ptr, lay.n_weights, self._ws.data_ptr(),
+                                         self._ws.numel(), self._norm2.data_ptr(), st), "grad_sqnorm")
         self._steps_dirty = True      # the device counter advances only if the kernel applies the update
         lr = group["lr"]
         _lib.check(lib.b200b_adamw_fused(
-            b._flat.data_ptr(), g.data_ptr(), self._m.data_ptr(), self._v.data_ptr(), b._w16.data_ptr(), lay.total,
+            b._flat.data_ptr(), g.data_ptr(), g16_ptr, self._m.data_ptr(), self._v.data_ptr(), b._w16.data_ptr(), lay.total,
             lay.n_weights, self._norm2.data_ptr(), float(self.max_grad_norm or 0.0),
             None if grad_scale is None else grad_scale.data_ptr(), None if found_inf is None else found_inf.data_ptr(),
             float(lr.item() if torch.is_tensor(lr) else lr), group["betas"][0], group["betas"][1], group["eps"],

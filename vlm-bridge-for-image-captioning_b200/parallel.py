@@ -45,7 +45,8 @@ class GradBucketReducer:
 
     def __init__(self, process_group: Optional[dist.ProcessGroup] = None, bucket_bytes: int = 32 << 20,
                  grad_dtype: torch.dtype = torch.bfloat16, backend: str = "auto", nvls_blocks: int = 32,
-                 nvls_threads: int = 512, exclusive_sms: bool = False, fp32_multicast: bool = False):
+                 nvls_threads: int = 512, exclusive_sms: bool = False, fp32_multicast: bool = False,
+                 nvls_unroll: int = 4, materialize_fp32: bool = True, timeout_s: Optional[int] = None):
         if grad_dtype not in (torch.bfloat16, torch.float32):
             raise ValueError("grad_dtype must be torch.bfloat16 or torch.float32")
         if backend not in ("auto", "nvls", "nccl"):
@@ -65,6 +66,22 @@ class GradBucketReducer:
         self.nvls_threads = int(nvls_threads)
         self.exclusive_sms = bool(exclusive_sms) and self.nvls_blocks % 2 == 0
         self.fp32_multicast = bool(fp32_multicast)   # False: bf16 result in place + a separate bf16 -> fp32 pass
+        if nvls_unroll not in (4, 8, 16):
+            raise ValueError("nvls_unroll must be 4, 8 or 16")
+        self.nvls_unroll = int(nvls_unroll)
+        # False (bf16 exchange only): the averaged weight gradients STAY in the bf16 arena -- no bf16 -> fp32 pass
+        # (0.95 GB of HBM traffic per step), the weights' `.grad` are not set; `BridgeAdamW` reads the arena directly
+        # and `BridgeLite.materialize_grads()` produces fp32 `.grad` on demand
+        self.materialize_fp32 = bool(materialize_fp32) or not self.wgrad_bf16
+        # a rank may legitimately be seconds late (checkpoint write, validation, first-step initialisation): the
+        # exchange waits as long as the process group would
+        if timeout_s is None:
+            try:
+                timeout_s = int(dist.distributed_c10d._get_default_timeout(dist.get_backend(process_group)).total_seconds())
+            except Exception:  # noqa: BLE001
+                timeout_s = 600
+        self.timeout_s = max(1, int(timeout_s))
+        self._err_word: Optional[torch.Tensor] = None
         self.diag_skip_convert = False  # diagnostics only: leaves .grad of the weights unwritten (timing what the pass costs)
         self._nvls = None               # (comm struct, symmetric byte buffer, flag buffer, handles)
         self.trace: Optional[list] = None   # set to [] to record per-bucket CUDA events (diagnostics)
@@ -93,7 +110,8 @@ class GradBucketReducer:
         kind = "bf16 buckets + fp32 vectors" if self.wgrad_bf16 else "fp32 buckets"
         how = (f"own NVLS multimem kernel ({self.nvls_blocks} CTAs x {self.nvls_threads} threads"
                f"{' on SMs of their own' if self.exclusive_sms else ''}"
-               f"{', fp32 multicast into .grad' if self.fp32_multicast else ', bf16 in place + fp32 pass'})"
+               f", {self.nvls_unroll} x 16 B in flight per thread"
+               f"{', fp32 multicast into .grad' if self.fp32_multicast else (', bf16 in place + fp32 pass' if self.materialize_fp32 else ', bf16 in place, no fp32 pass (optimizer reads the bf16 arena)')})"
                if self.backend == "nvls" else ("NCCL" if self._nccl else dist.get_backend(self.group)))
         return (f"{how} all-reduce(avg), {kind}, >= {self.bucket_bytes >> 20} MiB per bucket, "
                 f"{self.buckets_per_step} collectives per step")
@@ -137,6 +155,10 @@ class GradBucketReducer:
         for q in range(self.world_size):
             comm.flags[q] = hflags.buffer_ptrs[q]
         comm.rank, comm.world = dist.get_rank(self.group), self.world_size
+        # pinned host word the kernel writes when a barrier wait expires (read by check_errors without a sync)
+        self._err_word = torch.zeros(1, dtype=torch.int32).pin_memory()
+        comm.timeout_s = self.timeout_s
+        comm.error_word = self._err_word.data_ptr()
         return dict(comm=comm, buf=buf, flags=flags, handles=(hbuf, hflags), n_weights=n_weights, total=total,
                     esize=esize, mc=int(hbuf.multicast_ptr), off16=bytes32,
                     epoch_dev=torch.zeros(1, dtype=torch.int32, device=device),
@@ -149,15 +171,29 @@ class GradBucketReducer:
         # collective number = (index within this step) + device counter advanced once per step by
         # finish(): identical for eager launches and for replays of a captured CUDA graph
         self._epoch += 1
-        flags = (_lib.NVLS_OUT_MULTICAST if out_multicast else 0) | (_lib.NVLS_EXCLUSIVE_SMS if self.exclusive_sms else 0)
+        flags = ((_lib.NVLS_OUT_MULTICAST if out_multicast else 0) | (_lib.NVLS_EXCLUSIVE_SMS if self.exclusive_sms else 0)
+                 | (self.nvls_unroll << 8))
         _lib.check(_lib.lib().b200b_allreduce_nvls(
             C.byref(self._nvls["comm"]), 0 if bf16 else 1, byte_offset, nbytes, 1.0 / self.world_size,
             C.c_void_p(out_multicast) if out_multicast else None, self._epoch, self._nvls["epoch_dev"].data_ptr(),
             self.nvls_blocks, self.nvls_threads, flags, self._post.cuda_stream),
             "allreduce_nvls")
 
+    def check_errors(self) -> None:
+        """Raises if an earlier collective of the nvls transport gave up waiting for a rank (`timeout_s`). The
+        kernel reports that through a pinned host word, so this costs no synchronisation; it is called at the
+        start and end of every backward, i.e. the failure surfaces one step late at the latest."""
+        w = self._err_word
+        if w is not None and int(w[0]) != 0:
+            code = int(w[0])
+            raise RuntimeError(f"gradient exchange (nvls): rank {dist.get_rank(self.group)} waited more than {self.timeout_s} s "
+                               f"for rank {(code & 0xff) - 1} (phase {(code >> 8) & 0xf}, block {code >> 12}); the gradients "
+                               "of that step are invalid. A rank is stalled or dead; raise `timeout_s` if ranks may "
+                               "legitimately skew that long")
+
     # -- protocol ------------------------------------------------------------------------------------
     def begin(self, arena32: torch.Tensor, arena16: Optional[torch.Tensor], n_weights: int) -> None:
+        self.check_errors()
         self._arena32, self._arena16, self._n_weights = arena32, arena16, n_weights
         self._pending, self._vec, self._works = None, None, []
         self._epoch = 0
@@ -194,7 +230,7 @@ class GradBucketReducer:
         lo, hi = self._pending
         self._pending = None
         src = self._arena16 if self._arena16 is not None else self._arena32
-        self._launch(src[lo:hi], lo, hi, convert=src.dtype == torch.bfloat16)
+        self._launch(src[lo:hi], lo, hi, convert=src.dtype == torch.bfloat16 and self.materialize_fp32)
 
     def vectors_ready(self, start: int, end: int) -> None:
         """fp32 bias / LayerNorm gradient ranges; merged and sent as one bucket by finish()."""
@@ -216,6 +252,7 @@ class GradBucketReducer:
             torch.cuda.current_stream().wait_stream(self._post)
         self._works.clear()
         self._arena32 = self._arena16 = None
+        self.check_errors()
 
     # -- one bucket ----------------------------------------------------------------------------------
     def _launch(self, chunk: torch.Tensor, lo: int, hi: int, convert: bool) -> None:
@@ -236,7 +273,7 @@ class GradBucketReducer:
                     # fp32 ranges of the symmetric .grad arena (bias / LayerNorm gradients, or everything
                     # with grad_dtype=float32): averaged in place
                     self._launch_nvls(4 * lo, (nbytes + 15) // 16 * 16, False)
-                elif self.fp32_multicast:
+                elif self.fp32_multicast and convert:
                     # bf16 bucket: reduced in the switch, broadcast as fp32 into every rank's .grad arena
                     self._launch_nvls(nv["off16"] + 2 * lo, nbytes, True, nv["mc"] + 4 * lo)
                 else:
@@ -245,7 +282,7 @@ class GradBucketReducer:
                     from . import _lib
 
                     self._launch_nvls(nv["off16"] + 2 * lo, nbytes, True)
-                    if not self.diag_skip_convert:
+                    if convert and not self.diag_skip_convert:
                         _lib.check(_lib.lib().b200b_bf16_to_f32(chunk.data_ptr(), self._arena32[lo:hi].data_ptr(), hi - lo,
                                                                 1.0, self._post.cuda_stream), "bf16_to_f32")
             if self.trace is not None:
@@ -301,7 +338,8 @@ def _nvls_available() -> bool:
 def enable_data_parallel(module, process_group=None, bucket_bytes: int = 32 << 20,
                          grad_dtype: torch.dtype = torch.bfloat16, backend: str = "auto",
                          nvls_blocks: int = 32, nvls_threads: int = 512, exclusive_sms: bool = False,
-                         fp32_multicast: bool = False) -> GradBucketReducer:
+                         fp32_multicast: bool = False, nvls_unroll: int = 4, materialize_fp32: bool = True,
+                         timeout_s: Optional[int] = None) -> GradBucketReducer:
     """Attach a bucketed all-reduce to `module` (a B200 BridgeLite). Returns the reducer.
 
     Defaults are the fastest configuration measured on B200 (profiles/r01_dp_transport_sweep.md): the
@@ -310,11 +348,22 @@ def enable_data_parallel(module, process_group=None, bucket_bytes: int = 32 << 2
     conversion pass, twice the broadcast bytes on the links); `exclusive_sms=True` sets `nvls_blocks`
     SMs aside for the exchange (CTA pairs claiming whole SMs, the persistent GEMMs limited to the
     rest via b200b_set_sm_limit until `disable_data_parallel`) -- interference drops to ~+10 % but a
-    handful of SMs cannot issue multimem requests fast enough (~13 GB/s per SM)."""
+    handful of SMs cannot issue multimem requests fast enough (~13 GB/s per SM at 4 units in flight per thread;
+    `nvls_unroll` 8 / 16 deepens that).
+
+    `materialize_fp32=False` (bf16 exchange): the averaged weight gradients stay in the bf16 arena, the weights'
+    `.grad` stay None, `BridgeAdamW` consumes the arena directly (same arithmetic: the fp32 `.grad` would hold
+    exactly these bf16 values) and `module.materialize_grads()` produces fp32 `.grad` tensors on demand -- for a
+    loop that needs them every step (GradScaler.unscale_, clip_grad_norm_, torch.optim.AdamW) keep the default.
+
+    `timeout_s`: how long a collective waits for a late rank before the step fails with a RuntimeError
+    (default: the process group's timeout). The transport cannot wait forever the way a host-side NCCL watchdog
+    does, because a spinning kernel cannot be cancelled; it reports through a pinned host word instead of
+    trapping, so the CUDA context survives."""
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised")
     reducer = GradBucketReducer(process_group, bucket_bytes, grad_dtype, backend, nvls_blocks, nvls_threads,
-                                exclusive_sms, fp32_multicast)
+                                exclusive_sms, fp32_multicast, nvls_unroll, materialize_fp32, timeout_s)
     module._bucket_hook = reducer
     if reducer.backend == "nvls" and reducer.exclusive_sms and reducer.world_size > 1 and torch.cuda.is_available():
         from . import _lib
