@@ -265,6 +265,11 @@ def workload_config(n_gpus: int) -> dict:
         "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single",
         "l2": "working set (0.95 GB fp32+bf16 weights, 0.63 GB grads, >= 0.25 GB activations) exceeds the 126 MB L2; no flush needed",
         "weights": "random init (reference Xavier scheme, seed 0); bf16 copies re-cast every step",
+        **({"gradients": "N > 1: bridge gradients averaged over ranks every step inside the backward (bf16 buckets over "
+                         "NVLink / NVSwitch); the step's result is the averaged gradient in the form the fused optimizer "
+                         "(BridgeAdamW) consumes: bf16 arena for the 2-D weights, fp32 for biases / LayerNorm "
+                         "(--dp-fp32-grads adds the fp32 .grad materialisation pass); dp.parity_rel_err checks it against "
+                         "the all-gathered mean of the per-rank gradients"} if n_gpus > 1 else {}),
     }
 
 
@@ -308,7 +313,7 @@ def run_b200_arm(args) -> int:
                              backend=args.dp_backend, nvls_blocks=args.nvls_blocks, nvls_threads=args.nvls_threads,
                              bucket_bytes=args.bucket_mb << 20, exclusive_sms=args.nvls_exclusive,
                              fp32_multicast=args.nvls_fp32_multicast, nvls_unroll=args.nvls_unroll,
-                             materialize_fp32=not args.dp_bf16_arena)
+                             materialize_fp32=args.dp_fp32_grads)
         model._bucket_hook.diag_skip_convert = args.diag_dp_skip_convert
 
     def step(v, t):
@@ -653,6 +658,12 @@ def run_b200_arm(args) -> int:
                 line["fused_ce"] = bench_fused_ce(dev, peaks)
             except Exception as e:  # noqa: BLE001
                 line["fused_ce"] = {"error": repr(e)[:300]}
+        # ---- the bridge inside the unmodified reference training loop, N=1 only ----
+        if world == 1 and not args.no_inloop:
+            try:
+                line["inloop"] = bench_inloop(args.steps)
+            except Exception as e:  # noqa: BLE001
+                line["inloop"] = {"error": repr(e)[:300]}
         # ---- CPU baseline beside it (N=1 only) ---------------------------------------------------
         if world == 1 and not args.no_cpu_baseline:
             v, ms, cores, sample, kind = cpu_bridge_samples_per_s(steps=3, warmup=1, budget_s=25.0)
@@ -810,6 +821,80 @@ def bench_torch_library(model, vision_d, text_d, steps: int) -> dict:
             "ms_per_step_by_launch_mode": {"eager": ms, "cuda graph replay": ms_graph, "graph_error": graph_err},
             "how": f"torch {torch.__version__}, torch.autocast(bfloat16): F.linear (cuBLASLt), F.layer_norm, "
                    "F.scaled_dot_product_attention, F.gelu, F.dropout; same weights, inputs, dropout p, loss"}
+
+
+def bench_inloop(steps: int) -> dict:
+    """BASELINE.json configs[1] / SURVEY.md 8d C2(i): the full training step of the UNMODIFIED reference
+    (`run_training_epoch`, core_training_loop.py:16-134: FullModel.forward under autocast(bf16), CE over the 256000-token
+    vocabulary, GradScaler, the per-parameter gradient-norm loop, clip_grad_norm_, AdamW) at batch 8, caption length
+    128, 224 px, random-init frozen DINOv2-large + Gemma-2-2B (full depth), timed with this repository's BridgeLite
+    swapped in and with the reference's own bridge. Wall clock per step (the loop synchronises with the host 50+
+    times per step). Needs oracle/_ref (oracle/make_ref.py) and transformers; reports why if it cannot run."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import inloop_harness as H
+
+    ok, why = H.available()
+    if not ok:
+        return {"unavailable": why}
+    from vlm_bridge_b200 import BridgeLite
+
+    with H.quiet():
+        model = H.build_full_model(BridgeLite, bridge_dropout=DROPOUT)
+    from vlm_bridge.training_strategy.core_training_loop import run_training_epoch
+
+    ours = model.bridge_module
+    ref_bridge = H.reference_bridge_cls()(vision_dim=D_VIS, language_dim=D_LANG, num_heads_cross=H_CROSS, dropout=DROPOUT).to("cuda")
+    ref_bridge.load_state_dict(ours.state_dict(), strict=True)
+    n = max(3, min(8, steps))
+    batches = H.make_batches(n, B_PER_GPU, L_TEXT)
+    out = {}
+    for name, bridge in (("b200_bridge", ours), ("reference_bridge_torch_eager", ref_bridge)):
+        model.bridge_module = bridge
+        ctx = H.training_context(model, batches[:2])
+        with H.quiet():
+            run_training_epoch(ctx, 0)                      # warm-up: 2 steps
+        ctx = H.training_context(model, batches, optimizer=ctx.optimizer)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with H.quiet():
+            loss = run_training_epoch(ctx, 1)
+        torch.cuda.synchronize()
+        out[name] = {"ms_per_step": (time.perf_counter() - t0) * 1e3 / n, "avg_loss": loss}
+    # the bridge's own share: fwd + bwd of the swapped-in module at the same shapes, device time
+    g = torch.Generator().manual_seed(1)
+    v = torch.randn(B_PER_GPU, N_VIS, D_VIS, generator=g).cuda()
+    t = torch.randn(B_PER_GPU, L_TEXT, D_LANG, generator=g).cuda().requires_grad_()
+    share = {}
+    for name, bridge in (("b200_bridge", ours), ("reference_bridge_torch_eager", ref_bridge)):
+        bridge.train()
+
+        def one():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = bridge(v, t)
+            y.float().square().mean().backward()
+
+        for _ in range(3):
+            one()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        share[name] = e0.elapsed_time(e1) / n
+    res = {"metric": "full training step of the unmodified reference loop, ms per step (wall clock)",
+           "config": f"B{B_PER_GPU} L{L_TEXT} 224 px, random-init frozen DINOv2-large (24 layers) + Gemma-2-2B (26 layers), "
+                     f"bf16 autocast + GradScaler + clip 0.3 + torch AdamW, {n} timed steps after 2 warm-up",
+           "whole_step_ms": {k: v_["ms_per_step"] for k, v_ in out.items()},
+           "avg_loss": {k: v_["avg_loss"] for k, v_ in out.items()},
+           "bridge_fwd_bwd_ms_same_shapes_eager": share,
+           "samples_per_s": {k: B_PER_GPU / (v_["ms_per_step"] * 1e-3) for k, v_ in out.items()}}
+    del model, ours, ref_bridge
+    torch.cuda.empty_cache()
+    return res
 
 
 def bench_fused_ce(dev, peaks) -> dict:
@@ -1027,6 +1112,7 @@ def main() -> int:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-train-step", action="store_true")
+    ap.add_argument("--no-inloop", action="store_true", help="skip the leg that runs the unmodified reference training loop")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches only (no CUDA-graph replay)")
     ap.add_argument("--graph-only", action="store_true", help="time the CUDA-graph replay only")
     ap.add_argument("--dp-backend", default="auto", choices=["auto", "nvls", "nccl"],
@@ -1035,9 +1121,10 @@ def main() -> int:
     ap.add_argument("--nvls-threads", type=int, default=512)
     ap.add_argument("--nvls-exclusive", action="store_true", help="reserve --nvls-blocks SMs for the exchange")
     ap.add_argument("--nvls-unroll", type=int, default=4, choices=[4, 8, 16], help="16-byte units in flight per thread")
-    ap.add_argument("--dp-bf16-arena", action="store_true",
-                    help="leave the averaged weight gradients in the bf16 arena (no bf16 -> fp32 pass; what BridgeAdamW "
-                         "consumes); default materialises fp32 .grad every step")
+    ap.add_argument("--dp-fp32-grads", action="store_true",
+                    help="N > 1: materialise fp32 .grad tensors every step (one more bf16 -> fp32 pass over 158 M elements). "
+                         "Default: the averaged weight gradients stay in the bf16 arena, which is what BridgeAdamW consumes "
+                         "(module.materialize_grads() produces fp32 .grad on demand)")
     ap.add_argument("--nvls-fp32-multicast", action="store_true", help="broadcast fp32 into .grad (no conversion pass)")
     ap.add_argument("--diag-dp-skip-convert", action="store_true",
                     help="diagnostics: skip the bf16 -> fp32 pass of the exchange (gradients are then incomplete)")
@@ -1051,7 +1138,7 @@ def main() -> int:
     if args.workload == "c5":
         global B_PER_GPU, N_VIS, WORKLOAD
         B_PER_GPU, N_VIS, WORKLOAD = 16, 1370, "C5"
-        args.no_decode = args.no_train_step = args.no_cpu_baseline = True
+        args.no_decode = args.no_train_step = args.no_cpu_baseline = args.no_inloop = True
     own_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)

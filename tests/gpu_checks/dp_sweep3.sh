@@ -11,12 +11,12 @@ except Exception as e:
     print("$name FAILED", e, flush=True)
 PY
 }
-run default
+run default --dp-fp32-grads
 run u16 --nvls-unroll 16
-run lazy --dp-bf16-arena
-run lazy_u16 --dp-bf16-arena --nvls-unroll 16
-run lazy_16x1024_u16 --dp-bf16-arena --nvls-unroll 16 --nvls-blocks 16 --nvls-threads 1024
-run lazy_8x1024_u16 --dp-bf16-arena --nvls-unroll 16 --nvls-blocks 8 --nvls-threads 1024
-run lazy_excl4_u16 --dp-bf16-arena --nvls-unroll 16 --nvls-blocks 4 --nvls-threads 1024 --nvls-exclusive
-run lazy_148x512_u8_b128 --dp-bf16-arena --nvls-unroll 8 --nvls-blocks 148 --nvls-threads 512 --bucket-mb 128
-run lazy_nccl --dp-bf16-arena --dp-backend nccl
+run lazy
+run lazy_u16 --nvls-unroll 16
+run lazy_16x1024_u16 --nvls-unroll 16 --nvls-blocks 16 --nvls-threads 1024
+run lazy_8x1024_u16 --nvls-unroll 16 --nvls-blocks 8 --nvls-threads 1024
+run lazy_excl4_u16 --nvls-unroll 16 --nvls-blocks 4 --nvls-threads 1024 --nvls-exclusive
+run lazy_148x512_u8_b128 --nvls-unroll 8 --nvls-blocks 148 --nvls-threads 512 --bucket-mb 128
+run lazy_nccl --dp-backend nccl

@@ -11,7 +11,7 @@ except Exception as e:
     print("$name FAILED", e, flush=True)
 PY
 }
-run default
-run lazy --dp-bf16-arena
-run lazy_nccl --dp-bf16-arena --dp-backend nccl
-run lazy_64x256 --dp-bf16-arena --nvls-blocks 64 --nvls-threads 256
+run default --dp-fp32-grads
+run lazy
+run lazy_nccl --dp-backend nccl
+run lazy_64x256 --nvls-blocks 64 --nvls-threads 256

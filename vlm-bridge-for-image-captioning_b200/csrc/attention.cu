@@ -883,7 +883,7 @@ static int launch_decode(const AttnParams& p, cudaStream_t stream) {
 }
 
 template <int HD>
-static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
+static int launch_bwd(const AttnParams& p, cudaStream_t stream, const b200b_attn_args* a) {
   using Cfg = AttnCfg<HD>;
   int rc = set_smem(attn_bwd_q_kernel<HD>, Cfg::kBwdQSmem, "attn_bwd_q");
   if (rc) return rc;
@@ -894,6 +894,11 @@ static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
              HD);
   rc = check_launch("attn_delta", stream);
   if (rc) return rc;
+  {
+    int taken = 0;
+    rc = attention_bwd_tc(a, p.delta, stream, &taken);
+    if (taken) return rc;
+  }
   dim3 gq((p.Lq + Cfg::kBM - 1) / Cfg::kBM, p.H, p.B);
   launch_pdl(kPdlAttn, attn_bwd_q_kernel<HD>, gq, dim3(128), Cfg::kBwdQSmem, stream, p);
   rc = check_launch("attn_bwd_q", stream);
@@ -932,6 +937,8 @@ static int validate_common(const b200b_attn_args* a, const char* what) {
 
 // attention_train_tc.cu: the tcgen05 forward; *taken = 1 when it launched (or failed), 0 when the shape is not its
 int attention_fwd_tc(const b200b_attn_args* a, cudaStream_t stream, int* taken);
+// the tcgen05 backward (dQ pass + dK / dV pass) given delta = rowsum(dO * O)
+int attention_bwd_tc(const b200b_attn_args* a, const float* delta, cudaStream_t stream, int* taken);
 
 static AttnParams make_params(const b200b_attn_args* a) {
   AttnParams p;
@@ -1016,9 +1023,9 @@ extern "C" int b200b_attention_bwd(const b200b_attn_args* a, void* stream_) {
   p.p_scr = reinterpret_cast<__nv_bfloat16*>(ws + off1);
   p.ds_scr = reinterpret_cast<__nv_bfloat16*>(ws + off1 + scr);
   switch (a->head_dim) {
-    case 64: return launch_bwd<64>(p, stream);
-    case 128: return launch_bwd<128>(p, stream);
-    default: return launch_bwd<288>(p, stream);
+    case 64: return launch_bwd<64>(p, stream, a);
+    case 128: return launch_bwd<128>(p, stream, a);
+    default: return launch_bwd<288>(p, stream, a);
   }
 }
 

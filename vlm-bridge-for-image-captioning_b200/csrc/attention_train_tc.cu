@@ -42,6 +42,8 @@ struct FwdTcParams {
   uint32_t drop_stream;
 };
 
+int attn_tc_mask();
+
 constexpr int kFBM = 128;            // query rows per CTA
 constexpr int kFBN = 64;             // keys per tile
 constexpr int kFThreads = 192;
@@ -316,6 +318,540 @@ static int launch_fwd_tc(const b200b_attn_args* a, cudaStream_t stream) {
   dim3 grid((a->len_q + kFBM - 1) / kFBM, a->heads, a->batch);
   launch_pdl(kPdlAttn, attn_fwd_tc_kernel<HD>, grid, dim3(kFThreads), Cfg::kSmemBytes, stream, tq, tk, tv, p);
   return check_launch("attn_fwd_tc", stream);
+}
+
+// =====================================================================================================
+// backward, query-major: dQ = scale * sum_t dS_t K_t           (autograd of bridge_module.py:132-139, 230-237)
+// =====================================================================================================
+// One CTA per (128 query rows, head, image). Q and dO stay resident (K-major A operands of S = Q K^T and
+// dP = dO V^T); K and V tiles of 64 keys are streamed through ONE buffer each (two 128 x HD tiles + two 64 x HD
+// tiles is all of the 227 KB at HD = 288): V is refilled as soon as dP(t) has been issued, K once dQ(t) -- which
+// reads the same K tile again as an MN-major B operand -- has completed. The softmax warps rebuild P from the
+// saved log-sum-exp, form dS = P * (dP - delta) with the forward's dropout mask and store it as bf16 into tensor
+// memory, from where it is the A operand of dQ += dS K. Nothing is spilled to global memory (the mma.sync
+// version wrote P and dS as [B, H, Lq, Lk] bf16 scratch for the key-major pass; here that pass recomputes them).
+struct BwdTcParams {
+  __nv_bfloat16* dq; long long lddq;
+  __nv_bfloat16* dk; long long lddk;
+  __nv_bfloat16* dv; long long lddv;
+  const float* lse2;                  // [B, H, Lq]
+  const float* delta;                 // [B, H, Lq]
+  int B, H, Lq, Lk, Lkp;
+  float scale, scale_log2;
+  DropoutCfg drop;
+  uint32_t drop_stream;
+};
+
+template <int HD>
+struct DqTcCfg {
+  static constexpr int kChunks = HD / 32;
+  static constexpr int kQBytes = kFBM * HD * 2;
+  static constexpr int kTileBytes = kFBN * HD * 2;
+  static constexpr int kN0 = HD > 256 ? 160 : HD;
+  static constexpr int kN1 = HD - kN0;
+  static constexpr int kSCol = 0;                     // TMEM: S [0, 64), dP [64, 128)
+  static constexpr int kDpCol = kFBN;
+  static constexpr int kDsCol = 2 * kFBN;             //       dS buffers [128, 192) (bf16 pairs: 32 columns each)
+  static constexpr int kDqCol = 3 * kFBN;             //       dQ [192, 192 + HD)
+  static constexpr uint32_t kTmemCols = (kDqCol + HD) <= 256 ? 256 : 512;
+  static constexpr size_t kSmemBytes = 2 * (size_t)kQBytes + 2 * (size_t)kTileBytes + 1024;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(kFThreads, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                      const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                      const BwdTcParams p) {
+  using Cfg = DqTcCfg<HD>;
+  extern __shared__ uint8_t smem_ftc_raw[];
+  // per key tile t (phase parity t & 1 unless indexed): k_full / v_full: tile landed; v_free: dP(t) issued and done;
+  // k_free: dQ(t) done; s_full: S(t) and dP(t) done; ds_full: dS(t) stored; dq_done[t & 1]: dQ(t) done
+  __shared__ __align__(8) uint64_t qdo_full, k_full, k_free, v_full, v_free, s_full, ds_full, dq_done[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kFBM, h = blockIdx.y, b = blockIdx.z;
+  const uint32_t s0 = (smem_u32(smem_ftc_raw) + 1023u) & ~1023u;
+  const uint32_t q_tile = s0, do_tile = s0 + Cfg::kQBytes;
+  const uint32_t k_tile = do_tile + Cfg::kQBytes, v_tile = k_tile + Cfg::kTileBytes;
+  const int nt = (p.Lk + kFBN - 1) / kFBN;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&qdo_full, 1);
+    mbar_init(&k_full, 1);
+    mbar_init(&k_free, 1);
+    mbar_init(&v_full, 1);
+    mbar_init(&v_free, 1);
+    mbar_init(&s_full, 1);
+    mbar_init(&ds_full, 4);
+    mbar_init(&dq_done[0], 1);
+    mbar_init(&dq_done[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_smem, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  if (warp == 5 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  pdl_launch_dependents();
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 5) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&qdo_full, 2 * Cfg::kQBytes);
+#pragma unroll
+      for (int c = 0; c < Cfg::kChunks; ++c) {
+        tma_load_4d(q_tile + (uint32_t)c * kFBM * 64, &tm_q, smem_u32(&qdo_full), c * 32, h, q0, b);
+        tma_load_4d(do_tile + (uint32_t)c * kFBM * 64, &tm_do, smem_u32(&qdo_full), c * 32, h, q0, b);
+      }
+      for (int t = 0; t < nt; ++t) {
+        if (t >= 1) mbar_wait(&k_free, (uint32_t)((t - 1) & 1));
+        mbar_arrive_expect_tx(&k_full, Cfg::kTileBytes);
+#pragma unroll
+        for (int c = 0; c < Cfg::kChunks; ++c)
+          tma_load_4d(k_tile + (uint32_t)c * kFBN * 64, &tm_k, smem_u32(&k_full), c * 32, h, t * kFBN, b);
+        if (t >= 1) mbar_wait(&v_free, (uint32_t)((t - 1) & 1));
+        mbar_arrive_expect_tx(&v_full, Cfg::kTileBytes);
+#pragma unroll
+        for (int c = 0; c < Cfg::kChunks; ++c)
+          tma_load_4d(v_tile + (uint32_t)c * kFBN * 64, &tm_v, smem_u32(&v_full), c * 32, h, t * kFBN, b);
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(kFBM, kFBN, false, false);
+      constexpr uint32_t idesc_q0 = umma_idesc_bf16(kFBM, Cfg::kN0, false, true);
+      constexpr uint32_t idesc_q1 = umma_idesc_bf16(kFBM, Cfg::kN1 > 0 ? Cfg::kN1 : 16, false, true);
+      mbar_wait(&qdo_full, 0);
+      for (int t = 0; t < nt; ++t) {
+        const uint32_t ph = (uint32_t)(t & 1);
+        // S(t) and dP(t): their TMEM buffers were read by the softmax warps before ds_full(t - 1), waited on below
+        mbar_wait(&k_full, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          umma_bf16(tmem_base + Cfg::kSCol, desc_sw64_kmajor(q_tile, kFBM, ks), desc_sw64_kmajor(k_tile, kFBN, ks), idesc_s,
+                    ks > 0);
+        mbar_wait(&v_full, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          umma_bf16(tmem_base + Cfg::kDpCol, desc_sw64_kmajor(do_tile, kFBM, ks), desc_sw64_kmajor(v_tile, kFBN, ks),
+                    idesc_s, ks > 0);
+        umma_commit(&s_full);
+        umma_commit(&v_free);
+        mbar_wait(&ds_full, ph);
+        tc_fence_after();
+        const uint32_t da = tmem_base + (uint32_t)(Cfg::kDsCol + (t & 1) * (kFBN / 2));
+        const uint32_t dd = tmem_base + (uint32_t)Cfg::kDqCol;
+#pragma unroll
+        for (int kc = 0; kc < kFBN / 16; ++kc) {
+          umma_bf16_tmem_a(dd, da + (uint32_t)(kc * 8), desc_sw64_mnmajor(k_tile, kFBN, 0, kc), idesc_q0, (t | kc) != 0);
+          if constexpr (Cfg::kN1 > 0)
+            umma_bf16_tmem_a(dd + (uint32_t)Cfg::kN0, da + (uint32_t)(kc * 8),
+                             desc_sw64_mnmajor(k_tile, kFBN, Cfg::kN0 / 32, kc), idesc_q1, (t | kc) != 0);
+        }
+        umma_commit(&dq_done[t & 1]);
+        umma_commit(&k_free);
+      }
+    }
+  } else {
+    const DropoutCfg drop = dropout_resolve(p.drop);
+    const int row = warp * 32 + lane;
+    const bool valid = q0 + row < p.Lq;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const size_t bh = (size_t)b * p.H + h;
+    const uint64_t ridx = (bh * p.Lq + (uint64_t)(q0 + row)) * (uint64_t)p.Lkp;
+    const float lse = valid ? p.lse2[bh * p.Lq + q0 + row] : 0.f;
+    const float del = valid ? p.delta[bh * p.Lq + q0 + row] : 0.f;
+    for (int t = 0; t < nt; ++t) {
+      mbar_wait(&s_full, (uint32_t)(t & 1));
+      tc_fence_after();
+      // dS buffer t & 1 was last read by dQ(t - 2)
+      if (t >= 2) mbar_wait(&dq_done[t & 1], (uint32_t)(((t >> 1) - 1) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < kFBN / 32; ++half) {
+        uint32_t sv[2][16], dv[2][16];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kSCol + half * 32 + g * 16), sv[g]);
+          tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kDpCol + half * 32 + g * 16), dv[g]);
+        }
+        tmem_ld_wait();
+        uint32_t w[16];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float ds[16];
+#pragma unroll
+          for (int j8 = 0; j8 < 2; ++j8) {
+            const int col0 = t * kFBN + half * 32 + g * 16 + j8 * 8;
+            uint4 bits = make_uint4(0, 0, 0, 0);
+            if (drop.thr != 0) bits = dropout_bits8(drop, p.drop_stream, (ridx + (uint64_t)col0) >> 3);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int j = j8 * 8 + e;
+              const float pr = (col0 + e < p.Lk) ? exp2f(__uint_as_float(sv[g][j]) * p.scale_log2 - lse) : 0.f;
+              float dpr = __uint_as_float(dv[g][j]);
+              if (drop.thr != 0) dpr = dropout_keep(bits, e, drop.thr) ? dpr * drop.scale : 0.f;
+              ds[j] = pr * (dpr - del);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[g * 8 + j] = pack_bf16(ds[2 * j], ds[2 * j + 1]);
+        }
+        tmem_st_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kDsCol + (t & 1) * (kFBN / 2) + half * 16), w);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ds_full);
+    }
+    mbar_wait(&dq_done[(nt - 1) & 1], (uint32_t)(((nt - 1) >> 1) & 1));
+    tc_fence_after();
+    __nv_bfloat16* dst = p.dq + ((size_t)b * p.Lq + (valid ? q0 + row : 0)) * p.lddq + (size_t)h * HD;
+#pragma unroll 1
+    for (int c0 = 0; c0 < HD; c0 += 32) {
+      uint32_t v0[16], v1[16];
+      tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kDqCol + c0), v0);
+      tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kDqCol + c0 + 16), v1);
+      tmem_ld_wait();
+      if (valid) {
+        uint4 u[4];
+        uint32_t* w = reinterpret_cast<uint32_t*>(u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          w[j] = pack_bf16(__uint_as_float(v0[2 * j]) * p.scale, __uint_as_float(v0[2 * j + 1]) * p.scale);
+          w[8 + j] = pack_bf16(__uint_as_float(v1[2 * j]) * p.scale, __uint_as_float(v1[2 * j + 1]) * p.scale);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + c0 + j * 8) = u[j];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// =====================================================================================================
+// backward, key-major: dV = Pd^T dO, dK = scale * dS^T Q, for query blocks of up to 128 rows (the training shapes)
+// =====================================================================================================
+// One CTA per (128 keys, head, image), TRANSPOSED formulation: S^T = K_j Q^T and dP^T = V_j dO^T put a key on every
+// TMEM lane, so P^T and dS^T come out in exactly the layout the tensor-memory A operand of dV = P^T dO and
+// dK = dS^T Q needs (lane = key = output row, columns = queries = contraction index); dO and Q are then read a second
+// time from the SAME shared-memory tiles as MN-major B operands. Three 128 x HD tiles are resident (K_j, later
+// overwritten by V_j; Q; dO) -- 221 KB at HD = 288. The bf16 P^T / dS^T overwrite the fp32 S^T / dP^T columns they
+// were computed from (slice by slice), which leaves room for one 128 x HD fp32 output: dV is produced and drained,
+// then dK.
+// A thread owns a key and walks over queries, but the dropout mask is indexed [query][8 consecutive keys per Philox
+// call] (the forward's natural order), so the 32 lanes of a warp -- 4 key groups -- share the work: each lane
+// evaluates Philox for 4 of the 32 (query, key group) pairs of a slice and the bits are exchanged with shuffles.
+template <int HD>
+struct DkvTcCfg {
+  static constexpr int kChunks = HD / 32;
+  static constexpr int kTileBytes = kFBM * HD * 2;     // 128 rows
+  static constexpr int kN0 = HD > 256 ? 160 : HD;
+  static constexpr int kN1 = HD - kN0;
+  static constexpr int kStCol = 0;                     // TMEM: S^T [0, 128) -> P^T bf16 in [0, 64)
+  static constexpr int kDptCol = 128;                  //       dP^T [128, 256) -> dS^T bf16 in [128, 192)
+  static constexpr int kOutCol = 192;                  //       dV, then dK: [192, 192 + HD)
+  static constexpr uint32_t kTmemCols = 512;
+  static constexpr size_t kSmemBytes = 3 * (size_t)kTileBytes + 1024;
+  static_assert(kOutCol + HD <= 512, "head dim");
+};
+
+template <int HD>
+__global__ void __launch_bounds__(kFThreads, 1)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                       const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                       const BwdTcParams p) {
+  using Cfg = DkvTcCfg<HD>;
+  extern __shared__ uint8_t smem_ftc_raw[];
+  __shared__ __align__(8) uint64_t kq_full, do_full, v_full, a_free, st_full, dpt_full, pds_full, dv_done, dv_drained, dk_done;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float lse_s[kFBM], del_s[kFBM];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j0 = blockIdx.x * kFBM, h = blockIdx.y, b = blockIdx.z;
+  const uint32_t s0 = (smem_u32(smem_ftc_raw) + 1023u) & ~1023u;
+  const uint32_t a_tile = s0, q_tile = s0 + Cfg::kTileBytes, do_tile = q_tile + Cfg::kTileBytes;
+  const size_t bh = (size_t)b * p.H + h;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&kq_full, 1);
+    mbar_init(&do_full, 1);
+    mbar_init(&v_full, 1);
+    mbar_init(&a_free, 1);
+    mbar_init(&st_full, 1);
+    mbar_init(&dpt_full, 1);
+    mbar_init(&pds_full, 4);
+    mbar_init(&dv_done, 1);
+    mbar_init(&dv_drained, 4);
+    mbar_init(&dk_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_smem, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  if (warp == 5 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x < kFBM) {
+    const bool ok = (int)threadIdx.x < p.Lq;
+    lse_s[threadIdx.x] = ok ? p.lse2[bh * p.Lq + threadIdx.x] : 0.f;
+    del_s[threadIdx.x] = ok ? p.delta[bh * p.Lq + threadIdx.x] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 5) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&kq_full, 2 * Cfg::kTileBytes);
+#pragma unroll
+      for (int c = 0; c < Cfg::kChunks; ++c) {
+        tma_load_4d(a_tile + (uint32_t)c * kFBM * 64, &tm_k, smem_u32(&kq_full), c * 32, h, j0, b);
+        tma_load_4d(q_tile + (uint32_t)c * kFBM * 64, &tm_q, smem_u32(&kq_full), c * 32, h, 0, b);
+      }
+      mbar_arrive_expect_tx(&do_full, Cfg::kTileBytes);
+#pragma unroll
+      for (int c = 0; c < Cfg::kChunks; ++c)
+        tma_load_4d(do_tile + (uint32_t)c * kFBM * 64, &tm_do, smem_u32(&do_full), c * 32, h, 0, b);
+      mbar_wait(&a_free, 0);      // S^T has consumed K_j: V_j takes its place
+      mbar_arrive_expect_tx(&v_full, Cfg::kTileBytes);
+#pragma unroll
+      for (int c = 0; c < Cfg::kChunks; ++c)
+        tma_load_4d(a_tile + (uint32_t)c * kFBM * 64, &tm_v, smem_u32(&v_full), c * 32, h, j0, b);
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(kFBM, kFBM, false, false);
+      constexpr uint32_t idesc_o0 = umma_idesc_bf16(kFBM, Cfg::kN0, false, true);
+      constexpr uint32_t idesc_o1 = umma_idesc_bf16(kFBM, Cfg::kN1 > 0 ? Cfg::kN1 : 16, false, true);
+      mbar_wait(&kq_full, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks)
+        umma_bf16(tmem_base + Cfg::kStCol, desc_sw64_kmajor(a_tile, kFBM, ks), desc_sw64_kmajor(q_tile, kFBM, ks), idesc_s,
+                  ks > 0);
+      umma_commit(&st_full);
+      umma_commit(&a_free);
+      mbar_wait(&do_full, 0);
+      mbar_wait(&v_full, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks)
+        umma_bf16(tmem_base + Cfg::kDptCol, desc_sw64_kmajor(a_tile, kFBM, ks), desc_sw64_kmajor(do_tile, kFBM, ks),
+                  idesc_s, ks > 0);
+      umma_commit(&dpt_full);
+      mbar_wait(&pds_full, 0);
+      tc_fence_after();
+      const uint32_t od = tmem_base + (uint32_t)Cfg::kOutCol;
+#pragma unroll
+      for (int kc = 0; kc < kFBM / 16; ++kc) {      // dV = Pd^T dO
+        umma_bf16_tmem_a(od, tmem_base + (uint32_t)(Cfg::kStCol + kc * 8), desc_sw64_mnmajor(do_tile, kFBM, 0, kc),
+                         idesc_o0, kc != 0);
+        if constexpr (Cfg::kN1 > 0)
+          umma_bf16_tmem_a(od + (uint32_t)Cfg::kN0, tmem_base + (uint32_t)(Cfg::kStCol + kc * 8),
+                           desc_sw64_mnmajor(do_tile, kFBM, Cfg::kN0 / 32, kc), idesc_o1, kc != 0);
+      }
+      umma_commit(&dv_done);
+      mbar_wait(&dv_drained, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int kc = 0; kc < kFBM / 16; ++kc) {      // dK = dS^T Q
+        umma_bf16_tmem_a(od, tmem_base + (uint32_t)(Cfg::kDptCol + kc * 8), desc_sw64_mnmajor(q_tile, kFBM, 0, kc),
+                         idesc_o0, kc != 0);
+        if constexpr (Cfg::kN1 > 0)
+          umma_bf16_tmem_a(od + (uint32_t)Cfg::kN0, tmem_base + (uint32_t)(Cfg::kDptCol + kc * 8),
+                           desc_sw64_mnmajor(q_tile, kFBM, Cfg::kN0 / 32, kc), idesc_o1, kc != 0);
+      }
+      umma_commit(&dk_done);
+    }
+  } else {
+    const DropoutCfg drop = dropout_resolve(p.drop);
+    const int row = warp * 32 + lane;          // key j0 + row lives on TMEM lane `row`
+    const int key = j0 + row;
+    const bool key_ok = key < p.Lk;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint64_t kgrp = (uint64_t)((j0 + warp * 32) >> 3) + (uint64_t)(lane >> 3);   // this lane's Philox key group
+    mbar_wait(&st_full, 0);
+    mbar_wait(&dpt_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < kFBM / 32; ++c) {      // 32 queries per slice
+      uint32_t sv[2][16], dv[2][16];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kStCol + c * 32 + g * 16), sv[g]);
+        tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kDptCol + c * 32 + g * 16), dv[g]);
+      }
+      tmem_ld_wait();
+      // dropout bits of the slice: lane L evaluates (query c*32 + r*8 + (L & 7), key group L >> 3) for r = 0..3
+      uint4 bits[4];
+      if (drop.thr != 0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const uint64_t qi = (uint64_t)(c * 32 + r * 8 + (lane & 7));
+          bits[r] = dropout_bits8(drop, p.drop_stream, ((bh * p.Lq + qi) * (uint64_t)p.Lkp >> 3) + kgrp);
+        }
+      }
+      uint32_t wp[16], wd[16];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        float pv[16], dsv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int qi = c * 32 + g * 16 + j;       // query index inside the block
+          float pr = (key_ok && qi < p.Lq) ? exp2f(__uint_as_float(sv[g][j]) * p.scale_log2 - lse_s[qi]) : 0.f;
+          float dpr = __uint_as_float(dv[g][j]);
+          float prd = pr;
+          if (drop.thr != 0) {
+            const int r = (g * 16 + j) >> 3, m = (g * 16 + j) & 7;
+            const int src = (lane & 24) | m;
+            uint4 bb;
+            bb.x = __shfl_sync(0xffffffffu, bits[r].x, src);
+            bb.y = __shfl_sync(0xffffffffu, bits[r].y, src);
+            bb.z = __shfl_sync(0xffffffffu, bits[r].z, src);
+            bb.w = __shfl_sync(0xffffffffu, bits[r].w, src);
+            const bool keep = dropout_keep(bb, lane & 7, drop.thr);
+            prd = keep ? pr * drop.scale : 0.f;
+            dpr = keep ? dpr * drop.scale : 0.f;
+          }
+          pv[j] = prd;
+          dsv[j] = pr * (dpr - del_s[qi]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          wp[g * 8 + j] = pack_bf16(pv[2 * j], pv[2 * j + 1]);
+          wd[g * 8 + j] = pack_bf16(dsv[2 * j], dsv[2 * j + 1]);
+        }
+      }
+      // in place: the bf16 slice [16c, 16c + 16) lies inside the fp32 columns [0, 32c + 32) already consumed
+      tmem_st_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kStCol + c * 16), wp);
+      tmem_st_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kDptCol + c * 16), wd);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&pds_full);
+    auto drain = [&](__nv_bfloat16* base, long long ld, float mul) {
+      __nv_bfloat16* dst = base + ((size_t)b * p.Lk + (key_ok ? key : 0)) * ld + (size_t)h * HD;
+#pragma unroll 1
+      for (int c0 = 0; c0 < HD; c0 += 32) {
+        uint32_t v0[16], v1[16];
+        tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kOutCol + c0), v0);
+        tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kOutCol + c0 + 16), v1);
+        tmem_ld_wait();
+        if (key_ok) {
+          uint4 u[4];
+          uint32_t* w = reinterpret_cast<uint32_t*>(u);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            w[j] = pack_bf16(__uint_as_float(v0[2 * j]) * mul, __uint_as_float(v0[2 * j + 1]) * mul);
+            w[8 + j] = pack_bf16(__uint_as_float(v1[2 * j]) * mul, __uint_as_float(v1[2 * j + 1]) * mul);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + c0 + j * 8) = u[j];
+        }
+      }
+    };
+    mbar_wait(&dv_done, 0);
+    tc_fence_after();
+    drain(p.dv, p.lddv, 1.0f);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&dv_drained);
+    mbar_wait(&dk_done, 0);
+    tc_fence_after();
+    drain(p.dk, p.lddk, p.scale);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <int HD>
+static int launch_bwd_tc(const b200b_attn_args* a, const float* delta, cudaStream_t stream) {
+  static bool attr_done = false;   // idempotent; a race only repeats the calls
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)DqTcCfg<HD>::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)DkvTcCfg<HD>::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_last_error("attention_bwd (tcgen05): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_done = true;
+  }
+  BwdTcParams p;
+  p.dq = reinterpret_cast<__nv_bfloat16*>(a->dq); p.lddq = a->lddq;
+  p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.lddk = a->lddk;
+  p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv); p.lddv = a->lddv;
+  p.lse2 = a->lse;
+  p.delta = delta;
+  p.B = a->batch; p.H = a->heads; p.Lq = a->len_q; p.Lk = a->len_k; p.Lkp = (a->len_k + 7) & ~7;
+  p.scale = 1.0f / sqrtf((float)HD);
+  p.scale_log2 = p.scale * 1.4426950408889634f;
+  p.drop_stream = a->dropout_stream;
+  p.drop = make_dropout_cfg(a->dropout_p, a->seed, &p.drop_stream);
+  CUtensorMap tq, td, tk, tv;
+  int rc;
+  // query-major pass: Q / dO blocks of 128 rows, K / V tiles of 64 keys
+  if ((rc = make_tmap_heads_sw64(&tq, a->q, a->ldq, HD, a->heads, a->len_q, a->batch, kFBM)) != B200B_OK) return rc;
+  if ((rc = make_tmap_heads_sw64(&td, a->d_o, a->lddo, HD, a->heads, a->len_q, a->batch, kFBM)) != B200B_OK) return rc;
+  if ((rc = make_tmap_heads_sw64(&tk, a->k, a->ldk, HD, a->heads, a->len_k, a->batch, kFBN)) != B200B_OK) return rc;
+  if ((rc = make_tmap_heads_sw64(&tv, a->v, a->ldv, HD, a->heads, a->len_k, a->batch, kFBN)) != B200B_OK) return rc;
+  dim3 gq((a->len_q + kFBM - 1) / kFBM, a->heads, a->batch);
+  launch_pdl(kPdlAttn, attn_bwd_dq_tc_kernel<HD>, gq, dim3(kFThreads), DqTcCfg<HD>::kSmemBytes, stream, tq, td, tk, tv, p);
+  if ((rc = check_launch("attn_bwd_dq_tc", stream)) != B200B_OK) return rc;
+  // key-major pass: K / V blocks of 128 keys
+  if ((rc = make_tmap_heads_sw64(&tk, a->k, a->ldk, HD, a->heads, a->len_k, a->batch, kFBM)) != B200B_OK) return rc;
+  if ((rc = make_tmap_heads_sw64(&tv, a->v, a->ldv, HD, a->heads, a->len_k, a->batch, kFBM)) != B200B_OK) return rc;
+  dim3 gk((a->len_k + kFBM - 1) / kFBM, a->heads, a->batch);
+  launch_pdl(kPdlAttn, attn_bwd_dkv_tc_kernel<HD>, gk, dim3(kFThreads), DkvTcCfg<HD>::kSmemBytes, stream, tq, td, tk, tv, p);
+  return check_launch("attn_bwd_dkv_tc", stream);
+}
+
+// Backward through the tcgen05 kernels when the shape qualifies (query blocks of at most 128 rows: the key-major pass
+// keeps one query block resident); `delta` = rowsum(dO * O) has been computed by the caller.
+int attention_bwd_tc(const b200b_attn_args* a, const float* delta, cudaStream_t stream, int* taken) {
+  *taken = 0;
+  if (!(attn_tc_mask() & 2) || a->len_q > kFBM) return B200B_OK;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) | reinterpret_cast<uintptr_t>(a->v) |
+                       reinterpret_cast<uintptr_t>(a->d_o) | reinterpret_cast<uintptr_t>(a->dq) |
+                       reinterpret_cast<uintptr_t>(a->dk) | reinterpret_cast<uintptr_t>(a->dv);
+  if ((al & 15) || (a->ldq % 8) || (a->ldk % 8) || (a->ldv % 8) || (a->lddo % 8) || (a->lddq % 8) || (a->lddk % 8) ||
+      (a->lddv % 8))
+    return B200B_OK;
+  int rc;
+  switch (a->head_dim) {
+    case 64: rc = launch_bwd_tc<64>(a, delta, stream); break;
+    case 128: rc = launch_bwd_tc<128>(a, delta, stream); break;
+    case 288: rc = launch_bwd_tc<288>(a, delta, stream); break;
+    default: return B200B_OK;
+  }
+  *taken = 1;
+  return rc;
 }
 
 // bit 0 = tcgen05 forward, bit 1 = tcgen05 backward where they apply (default 3); the environment variable
