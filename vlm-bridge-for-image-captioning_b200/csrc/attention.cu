@@ -25,6 +25,11 @@
 
 namespace b200b {
 
+// attention_train_tc.cu: the tcgen05 forward; *taken = 1 when it launched (or failed), 0 when the shape is not its
+int attention_fwd_tc(const b200b_attn_args* a, cudaStream_t stream, int* taken);
+// the tcgen05 backward (dQ pass + dK / dV pass) given delta = rowsum(dO * O)
+int attention_bwd_tc(const b200b_attn_args* a, const float* delta, cudaStream_t stream, int* taken);
+
 struct AttnParams {
   const __nv_bfloat16* q; long long ldq;
   const __nv_bfloat16* k; long long ldk;
@@ -934,11 +939,6 @@ static int validate_common(const b200b_attn_args* a, const char* what) {
   }
   return B200B_OK;
 }
-
-// attention_train_tc.cu: the tcgen05 forward; *taken = 1 when it launched (or failed), 0 when the shape is not its
-int attention_fwd_tc(const b200b_attn_args* a, cudaStream_t stream, int* taken);
-// the tcgen05 backward (dQ pass + dK / dV pass) given delta = rowsum(dO * O)
-int attention_bwd_tc(const b200b_attn_args* a, const float* delta, cudaStream_t stream, int* taken);
 
 static AttnParams make_params(const b200b_attn_args* a) {
   AttnParams p;
