@@ -315,6 +315,7 @@ def run_b200_arm(args) -> int:
                              fp32_multicast=args.nvls_fp32_multicast, nvls_unroll=args.nvls_unroll,
                              materialize_fp32=args.dp_fp32_grads)
         model._bucket_hook.diag_skip_convert = args.diag_dp_skip_convert
+        model._bucket_hook.diag_skip_exchange = args.diag_dp_skip_exchange
 
     def step(v, t):
         model._w16_key = None            # weights count as updated by the optimizer since last step
@@ -850,18 +851,28 @@ def bench_inloop(steps: int) -> dict:
     n = max(3, min(8, steps))
     batches = H.make_batches(n, B_PER_GPU, L_TEXT)
     out = {}
-    for name, bridge in (("b200_bridge", ours), ("reference_bridge_torch_eager", ref_bridge)):
+    legs = (("b200_bridge", ours), ("reference_bridge_torch_eager", ref_bridge))
+    opts = {}
+    for name, bridge in legs:                              # warm-up: 2 steps each (cuBLAS heuristics, allocator)
         model.bridge_module = bridge
         ctx = H.training_context(model, batches[:2])
         with H.quiet():
-            run_training_epoch(ctx, 0)                      # warm-up: 2 steps
-        ctx = H.training_context(model, batches, optimizer=ctx.optimizer)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        with H.quiet():
-            loss = run_training_epoch(ctx, 1)
-        torch.cuda.synchronize()
-        out[name] = {"ms_per_step": (time.perf_counter() - t0) * 1e3 / n, "avg_loss": loss}
+            run_training_epoch(ctx, 0)
+        opts[name] = ctx.optimizer
+    # the frozen models dominate the step (~95 %) and run-to-run variation is a few ms: the legs alternate and the
+    # fastest epoch of each is reported
+    for rep in range(3):
+        for name, bridge in legs:
+            model.bridge_module = bridge
+            ctx = H.training_context(model, batches, optimizer=opts[name])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            with H.quiet():
+                loss = run_training_epoch(ctx, 1 + rep)
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t0) * 1e3 / n
+            if name not in out or ms < out[name]["ms_per_step"]:
+                out[name] = {"ms_per_step": ms, "avg_loss": loss}
     # the bridge's own share: fwd + bwd of the swapped-in module at the same shapes, device time
     g = torch.Generator().manual_seed(1)
     v = torch.randn(B_PER_GPU, N_VIS, D_VIS, generator=g).cuda()
@@ -887,7 +898,7 @@ def bench_inloop(steps: int) -> dict:
         share[name] = e0.elapsed_time(e1) / n
     res = {"metric": "full training step of the unmodified reference loop, ms per step (wall clock)",
            "config": f"B{B_PER_GPU} L{L_TEXT} 224 px, random-init frozen DINOv2-large (24 layers) + Gemma-2-2B (26 layers), "
-                     f"bf16 autocast + GradScaler + clip 0.3 + torch AdamW, {n} timed steps after 2 warm-up",
+                     f"bf16 autocast + GradScaler + clip 0.3 + torch AdamW, best of 3 alternating epochs of {n} steps after 2 warm-up steps",
            "whole_step_ms": {k: v_["ms_per_step"] for k, v_ in out.items()},
            "avg_loss": {k: v_["avg_loss"] for k, v_ in out.items()},
            "bridge_fwd_bwd_ms_same_shapes_eager": share,
@@ -1040,7 +1051,48 @@ def bench_decode(model, dev, peaks, _lib) -> dict:
     cross_ms = sum(v for k, v in per_kernel.items() if k in ("attn_decode_packed", "attn_decode_tc"))
     gemm_ms = sum(v for k, v in per_kernel.items() if k.startswith("gemm_tcgen05"))
     bytes_total = sum(decode_bytes_per_step(DEC_B, s, N_VIS, position_rows=True) for s in range(1, DEC_STEPS + 1))
-    achieved = bytes_total / (cross_ms * 1e-3) / 1e9 if cross_ms > 0 else 0.0
+    achieved_eager = bytes_total / (cross_ms * 1e-3) / 1e9 if cross_ms > 0 else 0.0
+    # The same 128 cross-attention launches of one caption batch (block 0: 1 new position per step; block 1: the
+    # whole prefix; same kernels, same cache, same shapes) back to back in ONE CUDA graph, timed with CUDA events:
+    # the kernels' own duration, without the gaps an event pair sees between eager launches of a host-bound loop.
+    from vlm_bridge_b200 import ops
+    from vlm_bridge_b200.bridge import TC_DECODE_MIN_LEN
+    Hc, dk = H_CROSS, D_LANG // H_CROSS
+    qbuf = torch.randn(DEC_B * DEC_STEPS, D_LANG, generator=torch.Generator().manual_seed(5)).bfloat16().to(dev)
+    obuf = torch.empty_like(qbuf)
+
+    def cross_launches():
+        for s_ in range(1, DEC_STEPS + 1):
+            for blk, lq in ((0, 1), (1, s_)):
+                kw_ = dict(block_index=blk, num_blocks=N_BLOCKS, batch=DEC_B, heads=Hc, len_q=lq, len_k=N_VIS, head_dim=dk,
+                           out=obuf[:DEC_B * lq], want_lse=False)
+                if lq >= TC_DECODE_MIN_LEN:
+                    ops.attention_decode_tc(qbuf[:DEC_B * lq], cache.kv_tc, **kw_)
+                else:
+                    ops.attention_decode_packed(qbuf[:DEC_B * lq], cache.kv_packed, **kw_)
+
+    cross_launches()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        cross_launches()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    cg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(cg):
+        cross_launches()
+    cg.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        cg.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    cross_ms_graph = e0.elapsed_time(e1) / 5
+    del cg
+    achieved = bytes_total / (cross_ms_graph * 1e-3) / 1e9
     gflop = decode_gemm_flops(DEC_B, DEC_STEPS, N_VIS)
     gemm_tf = gflop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     traffic, traffic_src = None, None
@@ -1069,8 +1121,12 @@ def bench_decode(model, dev, peaks, _lib) -> dict:
                    f"read-out, vocabulary {V}"),
         "roofline": {"bound": "hbm", "kernel": "attn_decode_kernel<288, packed> for <= 32 positions (all 64 block-0 launches: 1 position each), attn_decode_tc_kernel<288> above (the 128 cross-attention launches)", "achieved": achieved,
                      "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": traffic,
-                     "traffic_source": traffic_src, "algorithmic_bytes_total": bytes_total, "kernel_ms_total": cross_ms,
-                     "note": "event-timed between eager launches of one caption batch"},
+                     "traffic_source": traffic_src, "algorithmic_bytes_total": bytes_total, "kernel_ms_total": cross_ms_graph,
+                     "avg_launch_ms": cross_ms_graph / (2 * DEC_STEPS), "launches": 2 * DEC_STEPS,
+                     "timing": "the 128 launches of one caption batch back to back in one CUDA graph, CUDA events around 5 "
+                               "replays (the cache, 156 MB, exceeds the 126 MB L2)",
+                     "achieved_event_timed_in_eager_loop": achieved_eager, "kernel_ms_total_event_timed_in_eager_loop": cross_ms,
+                     "note": "the eager figure includes the idle gaps between launches of the host-bound Python loop"},
         "gemm_roofline": {"bound": "tensor", "kernel": "gemm_tcgen05 (prefix recompute: M = 32 * s rows)",
                           "achieved": gemm_tf, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
                           "frac": gemm_tf / peaks["bf16_burst"], "algorithmic_tflop_per_caption_batch": gflop / 1e12,
@@ -1128,6 +1184,8 @@ def main() -> int:
     ap.add_argument("--nvls-fp32-multicast", action="store_true", help="broadcast fp32 into .grad (no conversion pass)")
     ap.add_argument("--diag-dp-skip-convert", action="store_true",
                     help="diagnostics: skip the bf16 -> fp32 pass of the exchange (gradients are then incomplete)")
+    ap.add_argument("--diag-dp-skip-exchange", action="store_true",
+                    help="diagnostics: launch no collective (what writing the gradients into the symmetric arenas costs by itself)")
     ap.add_argument("--bucket-mb", type=int, default=32)
     ap.add_argument("--grad-dtype", default="bf16", choices=["bf16", "f32"],
                     help="dtype of the data-parallel weight-gradient exchange (N > 1)")

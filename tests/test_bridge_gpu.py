@@ -322,3 +322,44 @@ def test_invalidate_weight_cache_after_data_writes():
         m.invalidate_weight_cache()
         y1 = m(v, t)
     assert not torch.equal(y0, y1)
+
+
+def test_layer_classes_are_working_modules():
+    """The reference exports BridgeBlock / MultiHeadCrossAttention / MultiHeadSelfAttention as modules of their own
+    (model_architecture/__init__.py:22-27). Here their forwards run the library's kernels (inference only) and a
+    stack of two BridgeBlock forwards reproduces BridgeLite.forward and the oracle."""
+    from vlm_bridge_b200 import BridgeLite
+
+    cfg = dict(vision_dim=1024, language_dim=2304, num_blocks=2, num_heads_cross=8, num_heads_self=18)
+    sd = O.init_state_dict(8)
+    m = _make(cfg, sd).eval()
+    g = torch.Generator().manual_seed(88)
+    vision, text = torch.randn(2, 257, 1024, generator=g), torch.randn(2, 70, 2304, generator=g)
+    y_ref, blocks_ref = O.bridge_forward(sd, vision, text, return_blocks=True)
+    with torch.no_grad():
+        y = m(vision.cuda(), text.cuda())
+        x = text.cuda()
+        for blk in m.bridge_blocks:
+            x = blk(x, vision.cuda())
+        b0 = m.bridge_blocks[0]
+        xn = torch.nn.functional.layer_norm(text, (2304,), sd["bridge_blocks.0.ln_cross.weight"],
+                                            sd["bridge_blocks.0.ln_cross.bias"])
+        ca = b0.cross_attention(xn.cuda(), vision.cuda(), vision.cuda())
+        sa = b0.self_attention(xn.cuda())
+    assert _maxrel(x, y_ref) <= 2e-2 and _maxrel(x, y.cpu()) <= 1e-2
+    pre = "bridge_blocks.0.cross_attention."
+    k = O.linear(vision, sd[pre + "w_k.weight"], sd[pre + "w_k.bias"], False)
+    v = O.linear(vision, sd[pre + "w_v.weight"], sd[pre + "w_v.bias"], False)
+    q = O.linear(xn, sd[pre + "w_q.weight"], sd[pre + "w_q.bias"], False)
+    ca_ref = O.linear(O.attention(q, k, v, 8, False), sd[pre + "w_o.weight"], sd[pre + "w_o.bias"], False)
+    assert _maxrel(ca, ca_ref) <= 2e-2
+    pre = "bridge_blocks.0.self_attention."
+    qs, ks, vs = (O.linear(xn, sd[pre + f"w_{n}.weight"], sd[pre + f"w_{n}.bias"], False) for n in "qkv")
+    sa_ref = O.linear(O.attention(qs, ks, vs, 18, False), sd[pre + "w_o.weight"], sd[pre + "w_o.bias"], False)
+    assert _maxrel(sa, sa_ref) <= 2e-2
+    with pytest.raises(RuntimeError):
+        b0.self_attention(xn.cuda(), mask=torch.ones(2, 70, 70).cuda())
+    with pytest.raises(RuntimeError):
+        b0(text.cuda().requires_grad_(), vision.cuda())
+    with pytest.raises(RuntimeError):
+        b0(text, vision)

@@ -47,8 +47,17 @@ class MultiHeadCrossAttention(nn.Module):
         self.w_o = nn.Linear(d_model, query_dim)
         self.dropout = nn.Dropout(dropout)
 
-    def forward(self, *args, **kwargs):  # pragma: no cover - guidance only
-        raise RuntimeError("the B200 bridge fuses its sub-layers; call BridgeLite.forward (no per-layer path)")
+    def forward(self, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, mask=None) -> torch.Tensor:
+        """W_o * SDPA(W_q query, W_k key, W_v value) (reference bridge_module.py:75-120), inference only, on the
+        library's kernels (tcgen05 GEMMs + fused attention); output bf16-rounded values in fp32 like autocast."""
+        _layer_guard("MultiHeadCrossAttention", query, key, value, mask=mask)
+        B, Lq, _ = query.shape
+        Lk = key.shape[1]
+        q = _project(_rows_bf16(query), self.w_q)
+        k = _project(_rows_bf16(key), self.w_k)
+        v = k if (value is key and self.w_v is self.w_k) else _project(_rows_bf16(value), self.w_v)
+        o = _attend(q, k, v, B, Lq, Lk, self.num_heads, self.d_k)
+        return _project(o, self.w_o).float().view(B, Lq, self.query_dim)
 
 
 class MultiHeadSelfAttention(nn.Module):
@@ -65,8 +74,14 @@ class MultiHeadSelfAttention(nn.Module):
         self.w_o = nn.Linear(d_model, d_model)
         self.dropout = nn.Dropout(dropout)
 
-    def forward(self, *args, **kwargs):  # pragma: no cover - guidance only
-        raise RuntimeError("the B200 bridge fuses its sub-layers; call BridgeLite.forward (no per-layer path)")
+    def forward(self, x: torch.Tensor, mask=None) -> torch.Tensor:
+        """Non-causal, unmasked self-attention (reference bridge_module.py:178-222), inference only."""
+        _layer_guard("MultiHeadSelfAttention", x, mask=mask)
+        B, L, _ = x.shape
+        x16 = _rows_bf16(x)
+        q, k, v = _project(x16, self.w_q), _project(x16, self.w_k), _project(x16, self.w_v)
+        o = _attend(q, k, v, B, L, L, self.num_heads, self.d_k)
+        return _project(o, self.w_o).float().view(B, L, self.d_model)
 
 
 class BridgeBlock(nn.Module):
@@ -92,8 +107,34 @@ class BridgeBlock(nn.Module):
         )
         self.ln_ffn = nn.LayerNorm(language_dim)
 
-    def forward(self, *args, **kwargs):  # pragma: no cover - guidance only
-        raise RuntimeError("the B200 bridge fuses its sub-layers; call BridgeLite.forward (no per-layer path)")
+    def forward(self, text_embeddings: torch.Tensor, vision_features: torch.Tensor) -> torch.Tensor:
+        """One block on its own (reference bridge_module.py:300-335), inference only: the three pre-LN residual
+        sub-layers through the library's LayerNorm, GEMM (GELU / residual epilogues) and attention kernels."""
+        from . import ops
+        _layer_guard("BridgeBlock", text_embeddings, vision_features)
+        B, L, D = text_embeddings.shape
+        x = text_embeddings.detach().to(torch.float32).reshape(B * L, D).contiguous()
+
+        def ln(t, m):
+            return ops.layernorm_fwd(t, m.weight.detach().float().contiguous(), m.bias.detach().float().contiguous())[0]
+
+        def out_proj(a16, linear, resid):
+            return ops.gemm(a16, _w16(linear), epilogue=ops.EPI_F32_BIAS_RESID, bias=linear.bias.detach().float().contiguous(),
+                            resid=resid)
+
+        ca, sa = self.cross_attention, self.self_attention
+        v16 = _rows_bf16(vision_features)
+        Nv = vision_features.shape[1]
+        q = _project(ln(x, self.ln_cross), ca.w_q)
+        o = _attend(q, _project(v16, ca.w_k), _project(v16, ca.w_v), B, L, Nv, ca.num_heads, ca.d_k)
+        x = out_proj(o, ca.w_o, x)
+        xn = ln(x, self.ln_self)
+        o = _attend(_project(xn, sa.w_q), _project(xn, sa.w_k), _project(xn, sa.w_v), B, L, L, sa.num_heads, sa.d_k)
+        x = out_proj(o, sa.w_o, x)
+        h, _u = ops.gemm(ln(x, self.ln_ffn), _w16(self.ffn[0]), epilogue=ops.EPI_BF16_BIAS_GELU,
+                         bias=self.ffn[0].bias.detach().float().contiguous())
+        x = out_proj(h, self.ffn[3], x)
+        return x.view(B, L, D)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -172,6 +213,46 @@ class _Layout:
         out.append((self.kv_w_start, self.block_w_start[0]))
         out.append((self.kv_b_start, self.block_v_start[0]))
         return out
+
+
+# ------------------------------------------------------------------------------------------------
+# per-layer forwards (inference only): the reference exports these classes as working modules
+# (model_architecture/__init__.py:22-27). Training goes through BridgeLite's fused autograd node; the
+# layers on their own run the same kernels through the thin op wrappers, without autograd.
+# ------------------------------------------------------------------------------------------------
+def _layer_guard(name: str, *tensors: torch.Tensor, mask=None) -> None:
+    if mask is not None:
+        raise RuntimeError(f"{name}: attention masks are not built (the bridge never passes one: "
+                           "bridge_module.py:317-322,327)")
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError(f"{name} (B200) runs on CUDA only: there is no CPU fallback")
+    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+        raise RuntimeError(f"{name}.forward on its own is inference-only (wrap it in torch.no_grad()); training runs "
+                           "through BridgeLite.forward, which fuses the layers into one autograd node")
+
+
+def _w16(linear: nn.Linear) -> torch.Tensor:
+    return linear.weight.detach().to(torch.bfloat16).contiguous()
+
+
+def _rows_bf16(x: torch.Tensor) -> torch.Tensor:
+    from . import ops
+    x2 = x.detach().reshape(-1, x.shape[-1])
+    return x2.contiguous() if x2.dtype == torch.bfloat16 else ops.cast_bf16(x2.to(torch.float32).contiguous())
+
+
+def _project(x16: torch.Tensor, linear: nn.Linear) -> torch.Tensor:
+    from . import ops
+    return ops.gemm(x16, _w16(linear), bias=linear.bias.detach().float().contiguous())
+
+
+def _attend(q16, k16, v16, batch, len_q, len_k, heads, d_k) -> torch.Tensor:
+    from . import ops
+    if d_k not in (64, 128, 288):
+        raise RuntimeError(f"attention kernels are built for head dims 64 / 128 / 288, not {d_k}")
+    o, _ = ops.attention_fwd(q16, k16, v16, batch=batch, heads=heads, len_q=len_q, len_k=len_k, head_dim=d_k)
+    return o
 
 
 class _BridgeDims(C.Structure):

@@ -83,6 +83,7 @@ class GradBucketReducer:
         self.timeout_s = max(1, int(timeout_s))
         self._err_word: Optional[torch.Tensor] = None
         self.diag_skip_convert = False  # diagnostics only: leaves .grad of the weights unwritten (timing what the pass costs)
+        self.diag_skip_exchange = False  # diagnostics only: no collective is launched (gradients stay local, in the same arenas)
         self._nvls = None               # (comm struct, symmetric byte buffer, flag buffer, handles)
         self.trace: Optional[list] = None   # set to [] to record per-bucket CUDA events (diagnostics)
         self._t0 = None
@@ -257,6 +258,9 @@ class GradBucketReducer:
     # -- one bucket ----------------------------------------------------------------------------------
     def _launch(self, chunk: torch.Tensor, lo: int, hi: int, convert: bool) -> None:
         nbytes = chunk.numel() * chunk.element_size()
+        if self.diag_skip_exchange:
+            self.buckets_per_step += 1
+            return
         if self.backend == "nvls":
             self.bytes_reduced += nbytes
             self.bytes_per_step += nbytes
