@@ -493,12 +493,13 @@ class BridgeLite(nn.Module):
                            heads_self=self.num_heads_self, num_blocks=self.num_blocks, flags=flags)
 
     # -- vision K/V (shared with the decode cache) -------------------------------------------------
-    def project_vision_kv(self, vision_features: torch.Tensor, out=None):
+    def project_vision_kv(self, vision_features: torch.Tensor, out=None, _weights_current: bool = False):
         """K/V of every block for `vision_features` [B, Nv, vision_dim] -> (vision_bf16, kv bf16
         [B*Nv, num_blocks*2*language_dim]). Reference: bridge_module.py:99-100. `out=(vision_bf16, kv)`
         writes into existing tensors of those shapes."""
-        self._ensure_flat()
-        self._refresh_bf16()
+        if not _weights_current:        # _run_forward has just refreshed them (under graph capture a second call
+            self._ensure_flat()         # would record a second 158 M-element cast into the graph)
+            self._refresh_bf16()
         v = vision_features.detach().to(device=self._flat.device, dtype=torch.float32).contiguous()
         B, Nv, Dv = v.shape
         if Dv != self.vision_dim:
@@ -586,7 +587,7 @@ class BridgeLite(nn.Module):
         if kv_cache is None:
             if vision.dim() != 3 or vision.shape[0] != B:
                 raise RuntimeError("vision_features must be [B, Nv, vision_dim] with the text batch size")
-            vb, kv = self.project_vision_kv(vision)
+            vb, kv = self.project_vision_kv(vision, _weights_current=True)
             Nv = vision.shape[1]
         else:
             vb, kv, Nv = None, kv_cache.kv, kv_cache.len_vision
