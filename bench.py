@@ -613,12 +613,12 @@ def run_b200_arm(args) -> int:
         gflops = gemm_flops_per_step(B_PER_GPU, L_TEXT, N_VIS)
         achieved = gflops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "r01_ncu_gemm_step_v8.json")
+        tp = os.path.join(ROOT, "profiles", "r02_ncu_step_full.json")
         if os.path.exists(tp) and WORKLOAD == "C2":
             with open(tp) as f:
                 traffic = json.load(f)["summary"]["dram_bytes_per_launch_avg"]
-            traffic_src = ("profiles/r01_ncu_gemm_step_v8.json: dram__bytes_read.sum + dram__bytes_write.sum of the 38 GEMM "
-                           "launches of one step (ncu --set full), average per launch")
+            traffic_src = ("profiles/r02_ncu_step_full.json: dram__bytes_read.sum + dram__bytes_write.sum of the 38 GEMM "
+                           "launches of one step (ncu --set full capture of this round), average per launch")
         line["roofline"] = {
             "bound": "tensor", "kernel": "+".join(sorted(gemm_names)), "achieved": achieved, "peak": peaks["bf16_burst"],
             "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"],
