@@ -99,3 +99,85 @@ def test_dp_gradients_match_average_of_shards():
             assert buckets >= 5
         assert r["bf16"][3] < 0.51 * r["f32"][3] + 4 * 200000
         assert r["nvls_bf16"][3] < 0.51 * r["nvls_f32"][3] + 4 * 200000
+
+
+def _skew_worker(rank, world, port, out):
+    import datetime
+    import time
+
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev,
+                            timeout=datetime.timedelta(seconds=90))
+    from vlm_bridge_b200 import BridgeLite
+    from vlm_bridge_b200.parallel import broadcast_parameters, enable_data_parallel
+
+    torch.manual_seed(0)
+    m = BridgeLite(dropout=0.0).to(dev).train()
+    g = torch.Generator().manual_seed(1234 + rank)
+    v, t = torch.randn(1, 33, 1024, generator=g).to(dev), torch.randn(1, 24, 2304, generator=g).to(dev)
+    with torch.no_grad():
+        m(v, t)
+    broadcast_parameters(m)
+
+    def step():
+        for p in m.parameters():
+            p.grad = None
+        m(v, t).float().square().mean().backward()
+        torch.cuda.synchronize()
+
+    res = {}
+    # (1) a rank that is 3 s late is simply waited for when the limit is generous (the default is the process
+    #     group's timeout): same gradients on both ranks afterwards, no error
+    red = enable_data_parallel(m, backend="nvls", timeout_s=60)
+    step()                                   # sets the symmetric buffers up (contains a host-side barrier)
+    dist.barrier()
+    if rank == 1:
+        time.sleep(3.0)
+    step()
+    gsum = torch.cat([p.grad.reshape(-1) for p in m.parameters()]).double().sum()
+    both = [torch.zeros_like(gsum) for _ in range(world)]
+    dist.all_gather(both, gsum)
+    res["late_rank_waited_for"] = bool(both[0] == both[1])
+    red.check_errors()
+    # (2) with a 1 s limit the waiting rank gives the collective up and REPORTS it: RuntimeError at the end of the
+    #     backward (or at the next one), CUDA context intact
+    red.timeout_s = 1
+    red._nvls["comm"].timeout_s = 1
+    dist.barrier()
+    if rank == 1:
+        time.sleep(4.0)
+    err = None
+    try:
+        step()
+        step()
+    except RuntimeError as e:
+        err = str(e)
+    res["error"] = err
+    torch.cuda.synchronize()                                  # the context survived
+    res["context_alive"] = bool(torch.ones(4, device=dev).sum().item() == 4.0)
+    out[rank] = res
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_rank_skew_is_waited_for_and_a_timeout_is_reported_not_trapped():
+    """ADVICE (round 1): ranks skew by seconds around checkpoint writes / validation; the nvls transport must wait
+    like NCCL does and, past its limit, raise instead of destroying the CUDA context."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_skew_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+        res = dict(out)
+    assert res[0]["late_rank_waited_for"] and res[1]["late_rank_waited_for"]
+    assert res[0]["error"] is not None and "waited more than 1 s for rank 1" in res[0]["error"], res
+    assert res[0]["context_alive"] and res[1]["context_alive"]
