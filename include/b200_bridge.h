@@ -104,6 +104,18 @@ typedef struct b200b_gemm_args {
 
 int b200b_gemm(const b200b_gemm_args* args, void* stream);
 
+/* The data gradient and the weight gradient of one Linear (dX = dY W, dW = dY^T X: autograd of
+ * bridge_module.py:98,118,196-198,216) in ONE persistent launch. `dgrad` must be the dgrad form (a_major 0,
+ * b_major 1, B200B_EPI_BF16_BIAS without bias), `wgrad` the wgrad form (a_major 1, b_major 1, B200B_EPI_F32 with
+ * beta 0 or B200B_EPI_BF16_BIAS without bias); when both fit 256 x 128 pair tiles their 72 + 162 tiles (the
+ * 2304-wide projections at 1024 rows) run as one grouped tile list -- one launch ramp, 70 k-block units per CTA pair
+ * instead of one exposed tile and 2.2 waves. Any other pair of argument sets is executed as b200b_gemm(wgrad) then
+ * b200b_gemm(dgrad). Results are bit-equal to the two separate launches.
+ * b200b_gemm_set_dual(0) forces the two-launch form (A/B measurements, tests); returns the previous setting; < 0
+ * only queries. Environment: B200B_GEMM_DUAL. */
+int b200b_gemm_dual(const b200b_gemm_args* dgrad, const b200b_gemm_args* wgrad, void* stream);
+int b200b_gemm_set_dual(int on);
+
 /* ------------------------------------------------------------------------------------------- *
  * Row kernels (HBM-bound, vectorised): LayerNorm and the reductions / casts around it.
  * ------------------------------------------------------------------------------------------- */

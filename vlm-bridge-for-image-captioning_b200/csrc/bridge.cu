@@ -159,6 +159,24 @@ static int gemm(const void* a, int a_major, long long lda, const void* b, int b_
   return b200b_gemm(&g, st);
 }
 
+// dX = dY W (bf16 [rows, n_in]) and dW = dY^T X ([n_out, n_in], fp32 or bf16 by `wgrad_epi`) of one Linear as one grouped
+// launch where both fit 256 x 128 pair tiles (b200b_gemm_dual), else as two launches
+static int grad_pair(const void* dy, long long lddy, const void* w, const void* x, long long ldx, int rows, int n_out,
+                     int n_in, void* dx, long long lddx, void* dw, int wgrad_epi, cudaStream_t st) {
+  b200b_gemm_args dg, wg;
+  memset(&dg, 0, sizeof(dg));
+  memset(&wg, 0, sizeof(wg));
+  dg.a = dy; dg.a_major = 0; dg.lda = lddy;            // A = dY [rows, n_out]
+  dg.b = w; dg.b_major = 1; dg.ldb = n_in;             // B = W stored [n_out (k), n_in (n)]
+  dg.m = rows; dg.n = n_in; dg.k = n_out;
+  dg.epilogue = B200B_EPI_BF16_BIAS; dg.out = dx; dg.ldo = lddx;
+  wg.a = dy; wg.a_major = 1; wg.lda = lddy;            // A = dY stored [rows (k), n_out (m)]
+  wg.b = x; wg.b_major = 1; wg.ldb = ldx;              // B = X stored [rows (k), n_in (n)]
+  wg.m = n_out; wg.n = n_in; wg.k = rows;
+  wg.epilogue = wgrad_epi; wg.out = dw; wg.ldo = n_in;
+  return b200b_gemm_dual(&dg, &wg, st);
+}
+
 static int attn(bool bwd, const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                 void* o, long long ldo, float* lse, const void* d_o, void* dq, long long lddq, void* dk, long long lddk,
                 void* dv, long long lddv, void* ws, size_t ws_bytes, int B, int H, int Lq, int Lk, int hd, float p,
@@ -343,35 +361,29 @@ extern "C" int b200b_bridge_block_backward(const b200b_bridge_dims* dims, int i,
   fin.add(ws.p_lnf + D, g->ln_f_g, D, rchunks, 3LL * D);
   fin.add(ws.p_lnf + 2 * D, g->bo_s, D, rchunks, 3LL * D);
   // ---- self-attention ----
-  B200B_TRY(gemm(ws.dy, 1, D, s.o2, 1, D, D, D, T, EW, g->wo_s, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  B200B_TRY(grad_pair(ws.dy, D, w->wo_s, s.o2, D, T, D, D, ws.dattn, D, g->wo_s, EW, st));
   ready(g->wo_s, (long long)D * D);
-  B200B_TRY(gemm(ws.dy, 0, D, w->wo_s, 1, D, T, D, D, EB, ws.dattn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
   B200B_TRY(attn(true, s.qkv, 3 * D, s.qkv + D, 3 * D, s.qkv + 2 * D, 3 * D, s.o2, D, s.lse2, ws.dattn, ws.dqkv, 3 * D,
                  ws.dqkv + D, 3 * D, ws.dqkv + 2 * D, 3 * D, ws.attn_ws, ws.attn_ws_bytes, d.B, d.Hs, d.L, d.L, d.ds, p,
                  seed, (ds_self(i) | ind), st));
   B200B_TRY(b200b_colsum_partials(ws.dqkv, 3 * D, T, 3 * D, ws.p_dqkv, &ch, st));
   fin.add(ws.p_dqkv, g->bqkv_s, 3 * D, ch, 3LL * D);
-  B200B_TRY(gemm(ws.dqkv, 1, 3 * D, s.xn2, 1, D, 3 * D, D, T, EW, g->wqkv_s, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0,
-                 st));
+  B200B_TRY(grad_pair(ws.dqkv, 3 * D, w->wqkv_s, s.xn2, D, T, 3 * D, D, ws.dxn, D, g->wqkv_s, EW, st));
   ready(g->wqkv_s, 3LL * D * D);
-  B200B_TRY(gemm(ws.dqkv, 0, 3 * D, w->wqkv_s, 1, D, T, D, 3 * D, EB, ws.dxn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0,
-                 st));
   B200B_TRY(b200b_layernorm_bwd_fused(ws.dxn, s.x1, s.mean2, s.rstd2, w->ln_s_g, ws.dx, ws.dx, ws.dy, ws.p_lns, T, D, st));
   fin.add(ws.p_lns, g->ln_s_b, D, rchunks, 3LL * D);
   fin.add(ws.p_lns + D, g->ln_s_g, D, rchunks, 3LL * D);
   fin.add(ws.p_lns + 2 * D, g->bo_c, D, rchunks, 3LL * D);
   // ---- cross-attention ----
-  B200B_TRY(gemm(ws.dy, 1, D, s.o1, 1, D, D, D, T, EW, g->wo_c, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  B200B_TRY(grad_pair(ws.dy, D, w->wo_c, s.o1, D, T, D, D, ws.dattn, D, g->wo_c, EW, st));
   ready(g->wo_c, (long long)D * D);
-  B200B_TRY(gemm(ws.dy, 0, D, w->wo_c, 1, D, T, D, D, EB, ws.dattn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
   __nv_bfloat16* dq = ws.dqkv;  // [T, D]
   B200B_TRY(attn(true, s.q, D, kblk, ldkv, kblk + D, ldkv, s.o1, D, s.lse1, ws.dattn, dq, D, dkblk, ldkv, dkblk + D, ldkv,
                  ws.attn_ws, ws.attn_ws_bytes, d.B, d.Hc, d.L, d.Nv, d.dc, p, seed, (ds_cross(i) | ind), st));
   B200B_TRY(b200b_colsum_partials(dq, D, T, D, ws.p_dq, &ch, st));
   fin.add(ws.p_dq, g->bq_c, D, ch, D);
-  B200B_TRY(gemm(dq, 1, D, s.xn1, 1, D, D, D, T, EW, g->wq_c, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
+  B200B_TRY(grad_pair(dq, D, w->wq_c, s.xn1, D, T, D, D, ws.dxn, D, g->wq_c, EW, st));
   ready(g->wq_c, (long long)D * D);
-  B200B_TRY(gemm(dq, 0, D, w->wq_c, 1, D, T, D, D, EB, ws.dxn, D, nullptr, nullptr, nullptr, 0, 0.f, 0, 0, st));
   // ln_cross backward: d_in (if wanted) = dx + LN input gradient; dgamma / dbeta always
   B200B_TRY(b200b_layernorm_bwd_fused(ws.dxn, x_in, s.mean1, s.rstd1, w->ln_c_g, ws.dx, d_in, nullptr, ws.p_lnc, T, D, st));
   fin.add(ws.p_lnc, g->ln_c_b, D, rchunks, 3LL * D);

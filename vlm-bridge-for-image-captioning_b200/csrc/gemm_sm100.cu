@@ -614,6 +614,191 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Two independent GEMMs in ONE persistent launch: the data gradient and the weight gradient of a Linear
+// (dX = dY W and dW = dY^T X, autograd of bridge_module.py:98,118,196-198,216) share nothing but dY and do not
+// depend on each other. For the 2304-wide projections at T = 1024 rows each of them alone is a bad fit for 74
+// CTA pairs -- the dgrad is 72 pair tiles (one tile per pair: launch ramp, pipeline fill and the whole epilogue
+// exposed, ~5 us of MMA inside ~14 us), the wgrad 162 tiles (2.2 waves, 18 us) -- while together they are 234
+// tiles of 36 / 16 k-blocks = 70 k-block units per pair with one ramp and every epilogue but the last overlapped
+// by the next tile's main loop.
+//   problem 0: A K-major, B MN-major (dgrad form),  epilogue EPI0
+//   problem 1: A MN-major, B MN-major (wgrad form), epilogue EPI1
+// Both use 256 x 128 pair tiles. Tiles are numbered problem 0 first (its tiles are the long ones), then problem 1;
+// pair p takes tiles p, p + P, ... Per tile the three roles pick the problem's tensor maps, instruction
+// descriptor, A-operand descriptor form and epilogue; everything else is the single-problem kernel above, and a
+// tile's arithmetic is identical to it (same k order), so results are bit-equal to two separate launches.
+// ------------------------------------------------------------------------------------------------
+template <int EPI0, int EPI1>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_pair_dual_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_b0,
+                              const __grid_constant__ CUtensorMap tm_a1, const __grid_constant__ CUtensorMap tm_b1,
+                              const GemmKernelParams p0, const GemmKernelParams p1) {
+  constexpr int BLOCK_N = 128;
+  using Cfg = GemmPairCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kHalfN = BLOCK_N / 2;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+  __shared__ __align__(8) uint64_t empty_bar[kStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int pair_id = (int)cluster_id_x();
+  const int num_pairs = (int)cluster_nctaid_x();
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+  const uint32_t tfull0 = smem_u32(tmem_full_bar), tempty0 = smem_u32(tmem_empty_bar);
+  const uint32_t full0_even = full0 & 0xFEFFFFFFu;
+  const uint32_t tempty0_even = mapa_u32(tempty0, 0);
+
+  if (warp == kProducerWarp && lane == 0) {
+    tma_prefetch_desc(&tm_a0);
+    tma_prefetch_desc(&tm_b0);
+    tma_prefetch_desc(&tm_a1);
+    tma_prefetch_desc(&tm_b1);
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar[0], 1);
+    mbar_init(&tmem_full_bar[1], 1);
+    mbar_init(&tmem_empty_bar[0], 2 * 32 * kEpiWarps);
+    mbar_init(&tmem_empty_bar[1], 2 * 32 * kEpiWarps);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc_pair(&tmem_base_smem, Cfg::kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t tmem_base = tmem_base_smem;
+  const int tiles0 = p0.num_m_blocks * p0.num_n_blocks;
+  const int num_tiles = tiles0 + p1.num_m_blocks * p1.num_n_blocks;
+
+  if (warp == kProducerWarp) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      const bool second = tile >= tiles0;
+      const int lt = second ? tile - tiles0 : tile;
+      const int mb = second ? p1.num_m_blocks : p0.num_m_blocks;
+      const int nkb = second ? p1.num_k_blocks : p0.num_k_blocks;
+      const CUtensorMap* ta = second ? &tm_a1 : &tm_a0;
+      const CUtensorMap* tb = second ? &tm_b1 : &tm_b0;
+      const int m_idx = (lt % mb) * (2 * kBlockM) + (int)cta_rank * kBlockM;
+      const int n_idx = (lt / mb) * BLOCK_N + (int)cta_rank * kHalfN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait_a(empty0 + 8u * stage, phase ^ 1);
+        if (elect_one()) {
+          const uint32_t sa = smem0 + (uint32_t)stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint32_t fb = full0_even + 8u * stage;
+          if (leader) mbar_arrive_expect_tx_a(full0 + 8u * stage, 2 * Cfg::kStageBytes);
+          const int k_idx = kb * kBlockK;
+          if (!second) {
+            tma_load_2d_pair_a(sa, ta, fb, k_idx, m_idx);                       // A K-major: box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < kBlockM / 64; ++j) tma_load_2d_pair_a(sa + j * 8192, ta, fb, m_idx + 64 * j, k_idx);
+          }
+#pragma unroll
+          for (int j = 0; j < kHalfN / 64; ++j) tma_load_2d_pair_a(sb + j * 8192, tb, fb, n_idx + 64 * j, k_idx);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (leader) {
+      constexpr uint32_t idesc0 = umma_idesc_bf16(2 * kBlockM, BLOCK_N, false, true);
+      constexpr uint32_t idesc1 = umma_idesc_bf16(2 * kBlockM, BLOCK_N, true, true);
+      const uint64_t adesc_k = umma_smem_desc(smem0, DescConsts<false>::kLbo, 1024u);
+      const uint64_t adesc_mn = umma_smem_desc(smem0, DescConsts<true>::kLbo, 1024u);
+      const uint64_t bdesc0 = umma_smem_desc(smem0 + Cfg::kABytes, DescConsts<true>::kLbo, 1024u);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++iter) {
+        const bool second = tile >= tiles0;
+        const int nkb = second ? p1.num_k_blocks : p0.num_k_blocks;
+        const uint32_t idesc = second ? idesc1 : idesc0;
+        const uint64_t adesc0 = second ? adesc_mn : adesc_k;
+        const uint32_t a_kstep = second ? DescConsts<true>::kKStep16 : DescConsts<false>::kKStep16;
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        mbar_wait_a(tempty0 + 8u * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_a(full0 + 8u * stage, phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t soff16 = ((uint32_t)stage * Cfg::kStageBytes) >> 4;
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              umma_bf16_pair(d_tmem, desc_with_lo(adesc0, soff16 + k * a_kstep),
+                             desc_with_lo(bdesc0, soff16 + k * DescConsts<true>::kKStep16), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_pair_a(empty0 + 8u * stage, 0b11);
+            if (kb == nkb - 1) umma_commit_pair_a(tfull0 + 8u * acc, 0b11);
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int half = warp >> 2;
+    float* epi_stage =
+        reinterpret_cast<float*>(smem_gen + (size_t)kStages * Cfg::kStageBytes) + warp * 32 * kEpiLd;
+    const uint2 seed = make_uint2(0u, 0u);   // neither epilogue of a gradient pair draws dropout bits
+    int iter = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++iter) {
+      const bool second = tile >= tiles0;
+      const int lt = second ? tile - tiles0 : tile;
+      const int mb = second ? p1.num_m_blocks : p0.num_m_blocks;
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      const int m_idx = (lt % mb) * (2 * kBlockM) + (int)cta_rank * kBlockM;
+      const int n_idx = (lt / mb) * BLOCK_N;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      if (!second) {
+        EpiOperands<EPI0> ops;
+        drain_prefetch<BLOCK_N, EPI0>(p0, m_idx + quad * 32, n_idx, half, lane, ops);
+        mbar_wait_a(tfull0 + 8u * acc, acc_phase);
+        tc_fence_after();
+        drain_accumulator<BLOCK_N, EPI0>(p0, t_row, m_idx + quad * 32, n_idx, epi_stage, lane, half, ops, seed);
+      } else {
+        EpiOperands<EPI1> ops;
+        drain_prefetch<BLOCK_N, EPI1>(p1, m_idx + quad * 32, n_idx, half, lane, ops);
+        mbar_wait_a(tfull0 + 8u * acc, acc_phase);
+        tc_fence_after();
+        drain_accumulator<BLOCK_N, EPI1>(p1, t_row, m_idx + quad * 32, n_idx, epi_stage, lane, half, ops, seed);
+      }
+      tc_fence_before();
+      mbar_arrive_cluster_a(tempty0_even + 8u * acc);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == kMmaWarp) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -852,4 +1037,95 @@ extern "C" int b200b_gemm(const b200b_gemm_args* a, void* stream_) {
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
   if (block_n == 256) return dispatch_major<false, 256>(a->a_major, a->b_major, epi, ta, tb, p, grid, stream);
   return dispatch_major<false, 128>(a->a_major, a->b_major, epi, ta, tb, p, grid, stream);
+}
+
+// ---- the grouped dgrad + wgrad launch ------------------------------------------------------------
+namespace b200b {
+
+static void fill_params(const b200b_gemm_args* a, GemmKernelParams* p) {
+  p->m = a->m; p->n = a->n; p->k = a->k;
+  p->num_m_blocks = (a->m + 2 * kBlockM - 1) / (2 * kBlockM);
+  p->num_n_blocks = (a->n + 127) / 128;
+  p->num_k_blocks = (a->k + kBlockK - 1) / kBlockK;
+  p->out = a->out; p->ldo = a->ldo;
+  p->aux = nullptr; p->ldaux = 0;
+  p->bias = a->bias;
+  p->resid = nullptr; p->ldr = 0;
+  p->beta = a->beta;
+  p->drop_stream = 0;
+  p->drop = make_dropout_cfg(0.f, 0, nullptr);
+}
+
+template <int EPI1>
+static int launch_dual(const CUtensorMap& ta0, const CUtensorMap& tb0, const CUtensorMap& ta1, const CUtensorMap& tb1,
+                       const GemmKernelParams& p0, const GemmKernelParams& p1, int grid, cudaStream_t stream) {
+  static bool configured = false;  // benign race: attribute set is idempotent
+  auto kern = gemm_tcgen05_pair_dual_kernel<B200B_EPI_BF16_BIAS, EPI1>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmPairCfg<128>::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(gemm dual) failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  launch_pdl(kPdlGemm, kern, dim3(grid), dim3(kGemmThreads), GemmPairCfg<128>::kSmemBytes, stream, ta0, tb0, ta1, tb1, p0, p1);
+  return check_launch("gemm_tcgen05_pair_dual_kernel", stream);
+}
+
+static int g_gemm_dual = -1;   // 1 = grouped launch where it applies (default); B200B_GEMM_DUAL=0 / b200b_gemm_set_dual(0): two launches
+
+}  // namespace b200b
+
+extern "C" int b200b_gemm_set_dual(int on) {
+  if (g_gemm_dual < 0) {
+    const char* e = getenv("B200B_GEMM_DUAL");
+    g_gemm_dual = e ? atoi(e) : 1;
+  }
+  const int prev = g_gemm_dual;
+  if (on >= 0) g_gemm_dual = on;
+  return prev;
+}
+
+extern "C" int b200b_gemm_dual(const b200b_gemm_args* dgrad, const b200b_gemm_args* wgrad, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (dgrad == nullptr || wgrad == nullptr) {
+    set_last_error("gemm_dual: null argument");
+    return B200B_ERR_ARG;
+  }
+  int num_sms = 0;
+  int rc = device_sm_count(&num_sms);
+  if (rc != B200B_OK) return rc;
+  // The grouped kernel covers exactly the pair it was written for: dgrad form (A K-major, B MN-major, bf16 out, no
+  // bias) + wgrad form (A and B MN-major, fp32 or bf16 out, no bias, beta = 0), both on 256 x 128 pair tiles, no
+  // dropout. Anything else runs as the two launches it stands for.
+  const bool eligible =
+      b200b_gemm_set_dual(-1) != 0 && dgrad->a_major == 0 && dgrad->b_major == 1 && dgrad->epilogue == B200B_EPI_BF16_BIAS &&
+      dgrad->bias == nullptr && wgrad->a_major == 1 && wgrad->b_major == 1 &&
+      (wgrad->epilogue == B200B_EPI_F32 || wgrad->epilogue == B200B_EPI_BF16_BIAS) && wgrad->bias == nullptr &&
+      wgrad->beta == 0.f && dgrad->dropout_p == 0.f && wgrad->dropout_p == 0.f && dgrad->block_n == 0 && wgrad->block_n == 0 &&
+      dgrad->cta_group == 0 && wgrad->cta_group == 0 && dgrad->m > 0 && dgrad->n > 0 && dgrad->k > 0 && wgrad->m > 0 &&
+      wgrad->n > 0 && wgrad->k > 0 && (dgrad->n % 8) == 0 && (wgrad->n % 8) == 0 &&
+      choose_tile(dgrad->m, dgrad->n, num_sms).block_n == 128 && choose_tile(wgrad->m, wgrad->n, num_sms).block_n == 128 &&
+      aligned16(dgrad->a) && aligned16(dgrad->b) && aligned16(dgrad->out) && aligned16(wgrad->a) && aligned16(wgrad->b) &&
+      aligned16(wgrad->out) && (dgrad->lda % 8) == 0 && (dgrad->ldb % 8) == 0 && (dgrad->ldo % 8) == 0 &&
+      (wgrad->lda % 8) == 0 && (wgrad->ldb % 8) == 0 && (wgrad->ldo % (wgrad->epilogue == B200B_EPI_F32 ? 4 : 8)) == 0;
+  if (!eligible) {
+    rc = b200b_gemm(wgrad, stream_);
+    if (rc != B200B_OK) return rc;
+    return b200b_gemm(dgrad, stream_);
+  }
+  CUtensorMap ta0, tb0, ta1, tb1;
+  if ((rc = make_tmap_bf16(&ta0, dgrad->a, (uint64_t)dgrad->k, (uint64_t)dgrad->m, (uint64_t)dgrad->lda, kBlockM)) != B200B_OK) return rc;
+  if ((rc = make_tmap_bf16(&tb0, dgrad->b, (uint64_t)dgrad->n, (uint64_t)dgrad->k, (uint64_t)dgrad->ldb, kBlockK)) != B200B_OK) return rc;
+  if ((rc = make_tmap_bf16(&ta1, wgrad->a, (uint64_t)wgrad->m, (uint64_t)wgrad->k, (uint64_t)wgrad->lda, kBlockK)) != B200B_OK) return rc;
+  if ((rc = make_tmap_bf16(&tb1, wgrad->b, (uint64_t)wgrad->n, (uint64_t)wgrad->k, (uint64_t)wgrad->ldb, kBlockK)) != B200B_OK) return rc;
+  GemmKernelParams p0, p1;
+  fill_params(dgrad, &p0);
+  fill_params(wgrad, &p1);
+  const long long tiles = (long long)p0.num_m_blocks * p0.num_n_blocks + (long long)p1.num_m_blocks * p1.num_n_blocks;
+  const long long pairs = num_sms / 2;
+  const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);
+  if (wgrad->epilogue == B200B_EPI_F32) return launch_dual<B200B_EPI_F32>(ta0, tb0, ta1, tb1, p0, p1, grid, stream);
+  return launch_dual<B200B_EPI_BF16_BIAS>(ta0, tb0, ta1, tb1, p0, p1, grid, stream);
 }

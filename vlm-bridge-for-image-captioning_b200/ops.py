@@ -277,3 +277,23 @@ def attention_decode_tc(q: torch.Tensor, kv_tc: torch.Tensor, *, block_index: in
         q.data_ptr(), q.stride(0), kv_tc.data_ptr(), block_index, num_blocks, out.data_ptr(), out.stride(0),
         _ptr(lse), batch, heads, len_q, len_k, head_dim, _stream_ptr()), "attention_decode_tc")
     return out, lse
+
+
+def gemm_grad_pair(dy: torch.Tensor, w: torch.Tensor, x: torch.Tensor, *, wgrad_dtype: torch.dtype = torch.float32):
+    """dX = dY W (bf16 [rows, n_in]) and dW = dY^T X ([n_out, n_in], fp32 or bf16) of one Linear through
+    b200b_gemm_dual: ONE grouped persistent launch when both fit 256 x 128 pair tiles, two launches otherwise.
+    dy bf16 [rows, n_out], w bf16 [n_out, n_in], x bf16 [rows, n_in] (2-D views, any row pitch)."""
+    _need_cuda(dy, w, x)
+    rows, n_out = dy.shape
+    n_in = w.shape[1]
+    dx = torch.empty((rows, n_in), device=dy.device, dtype=torch.bfloat16)
+    dw = torch.empty((n_out, n_in), device=dy.device, dtype=wgrad_dtype)
+    dg = _lib.GemmArgs(a=dy.data_ptr(), b=w.data_ptr(), a_major=0, b_major=1, m=rows, n=n_in, k=n_out, lda=dy.stride(0),
+                       ldb=w.stride(0), epilogue=EPI_BF16_BIAS, block_n=0, out=dx.data_ptr(), ldo=dx.stride(0), aux=None,
+                       ldaux=0, bias=None, resid=None, ldr=0, beta=0.0, dropout_p=0.0, seed=0, dropout_stream=0, cta_group=0)
+    wg = _lib.GemmArgs(a=dy.data_ptr(), b=x.data_ptr(), a_major=1, b_major=1, m=n_out, n=n_in, k=rows, lda=dy.stride(0),
+                       ldb=x.stride(0), epilogue=EPI_F32 if wgrad_dtype == torch.float32 else EPI_BF16_BIAS, block_n=0,
+                       out=dw.data_ptr(), ldo=dw.stride(0), aux=None, ldaux=0, bias=None, resid=None, ldr=0, beta=0.0,
+                       dropout_p=0.0, seed=0, dropout_stream=0, cta_group=0)
+    _lib.check(_lib.lib().b200b_gemm_dual(C.byref(dg), C.byref(wg), _stream_ptr()), "gemm_dual")
+    return dx, dw
