@@ -1173,10 +1173,10 @@ def main() -> int:
     ap.add_argument("--graph-only", action="store_true", help="time the CUDA-graph replay only")
     ap.add_argument("--dp-backend", default="auto", choices=["auto", "nvls", "nccl"],
                     help="transport of the gradient exchange: own NVLS multimem kernel, or NCCL")
-    ap.add_argument("--nvls-blocks", type=int, default=32)
-    ap.add_argument("--nvls-threads", type=int, default=512)
+    ap.add_argument("--nvls-blocks", type=int, default=16)
+    ap.add_argument("--nvls-threads", type=int, default=1024)
     ap.add_argument("--nvls-exclusive", action="store_true", help="reserve --nvls-blocks SMs for the exchange")
-    ap.add_argument("--nvls-unroll", type=int, default=4, choices=[4, 8, 16], help="16-byte units in flight per thread")
+    ap.add_argument("--nvls-unroll", type=int, default=8, choices=[4, 8, 16], help="16-byte units in flight per thread")
     ap.add_argument("--dp-fp32-grads", action="store_true",
                     help="N > 1: materialise fp32 .grad tensors every step (one more bf16 -> fp32 pass over 158 M elements). "
                          "Default: the averaged weight gradients stay in the bf16 arena, which is what BridgeAdamW consumes "

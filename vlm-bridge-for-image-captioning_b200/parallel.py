@@ -44,9 +44,9 @@ class GradBucketReducer:
     """Driven by `BridgeLite._run_backward`: begin() -> weights_ready()* / flush() / vectors_ready()* -> finish()."""
 
     def __init__(self, process_group: Optional[dist.ProcessGroup] = None, bucket_bytes: int = 32 << 20,
-                 grad_dtype: torch.dtype = torch.bfloat16, backend: str = "auto", nvls_blocks: int = 32,
-                 nvls_threads: int = 512, exclusive_sms: bool = False, fp32_multicast: bool = False,
-                 nvls_unroll: int = 4, materialize_fp32: bool = True, timeout_s: Optional[int] = None):
+                 grad_dtype: torch.dtype = torch.bfloat16, backend: str = "auto", nvls_blocks: int = 16,
+                 nvls_threads: int = 1024, exclusive_sms: bool = False, fp32_multicast: bool = False,
+                 nvls_unroll: int = 8, materialize_fp32: bool = True, timeout_s: Optional[int] = None):
         if grad_dtype not in (torch.bfloat16, torch.float32):
             raise ValueError("grad_dtype must be torch.bfloat16 or torch.float32")
         if backend not in ("auto", "nvls", "nccl"):
@@ -58,7 +58,10 @@ class GradBucketReducer:
         self.wgrad_bf16 = grad_dtype == torch.bfloat16 and self.world_size > 1
         self._nccl = dist.get_backend(process_group) == "nccl"
         if backend == "auto":
-            backend = "nvls" if (self._nccl and self.world_size > 1 and _nvls_available()) else "nccl"
+            # measured on B200 (profiles/r02_dp_sweep6_2gpu.log, _sweep7_4gpu.log, _sweep8_8gpu.log): between two GPUs
+            # NCCL's point-to-point all-reduce disturbs the backward least (1.98 ms per step against 2.11 for the NVLS
+            # kernel); from four GPUs on the in-switch reduction wins (2.00 against 2.17 at N = 4, 2.01 at N = 8)
+            backend = "nvls" if (self._nccl and self.world_size > 2 and _nvls_available()) else "nccl"
         if backend == "nvls" and not (2 <= self.world_size <= 8):
             raise RuntimeError("the nvls transport needs 2..8 ranks on one NVSwitch domain")
         self.backend = backend
@@ -341,14 +344,16 @@ def _nvls_available() -> bool:
 
 def enable_data_parallel(module, process_group=None, bucket_bytes: int = 32 << 20,
                          grad_dtype: torch.dtype = torch.bfloat16, backend: str = "auto",
-                         nvls_blocks: int = 32, nvls_threads: int = 512, exclusive_sms: bool = False,
-                         fp32_multicast: bool = False, nvls_unroll: int = 4, materialize_fp32: bool = True,
+                         nvls_blocks: int = 16, nvls_threads: int = 1024, exclusive_sms: bool = False,
+                         fp32_multicast: bool = False, nvls_unroll: int = 8, materialize_fp32: bool = True,
                          timeout_s: Optional[int] = None) -> GradBucketReducer:
     """Attach a bucketed all-reduce to `module` (a B200 BridgeLite). Returns the reducer.
 
-    Defaults are the fastest configuration measured on B200 (profiles/r01_dp_transport_sweep.md): the
-    own NVLS kernel with 32 CTAs x 512 threads sharing SMs with the backward, bf16 result in place and
-    a bf16 -> fp32 pass per bucket. `fp32_multicast=True` broadcasts fp32 straight into `.grad` (no
+    Defaults are the fastest configuration measured on B200 (round 2: profiles/r02_dp_sweep6_2gpu.log,
+    r02_dp_sweep7_4gpu.log, r02_dp_sweep8_8gpu.log): from four ranks on the own NVLS kernel with 16 CTAs x 1024
+    threads x 8 units in flight sharing SMs with the backward (few, fat CTAs disturb fewer SMs: 2.01 ms per step at
+    N = 8 against 2.18 for 32 x 512 x 4), between two ranks NCCL; bf16 result in place and a bf16 -> fp32 pass per
+    bucket unless `materialize_fp32=False`. `fp32_multicast=True` broadcasts fp32 straight into `.grad` (no
     conversion pass, twice the broadcast bytes on the links); `exclusive_sms=True` sets `nvls_blocks`
     SMs aside for the exchange (CTA pairs claiming whole SMs, the persistent GEMMs limited to the
     rest via b200b_set_sm_limit until `disable_data_parallel`) -- interference drops to ~+10 % but a
