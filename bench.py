@@ -634,8 +634,10 @@ def run_b200_arm(args) -> int:
             "timing": "CUDA events recorded by the library after every launch on the launching stream, eager pass of "
                       f"{prof_steps} steps outside the timed region, median over steps",
         }
-        # ---- decode (config C4): cached vision K/V, bridge-only loop ------------------------------
-        if not args.no_decode:
+        # ---- decode (config C4): cached vision K/V, bridge-only loop. Decode shards images over the GPUs with no
+        # communication ("replicas only"), so the leg belongs to the N = 1 line; at N > 1 it runs only with --decode
+        # (the other ranks would sit in a collective while rank 0 works through it) --------------------------------
+        if not args.no_decode and (world == 1 or args.decode):
             try:
                 line["decode"] = bench_decode(model, dev, peaks, _lib)
             except Exception as e:  # noqa: BLE001
@@ -677,8 +679,12 @@ def run_b200_arm(args) -> int:
                     line["decode"]["cpu_baseline"] = {"error": repr(e)[:200]}
         emit(line)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # The last collective every rank takes part in is the barrier of sync_all() above; rank 0's remaining legs are
+        # local. No final barrier / destroy_process_group(): a default N = 2 run of this file was seen to hang in that
+        # tail after its JSON line had been written (profiles/r02 notes), so every rank leaves as soon as it is done --
+        # the line went out through os.write, nothing buffered is lost.
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 
@@ -1167,6 +1173,7 @@ def main() -> int:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--decode", action="store_true", help="run the decode leg at N > 1 as well (default: N = 1 only)")
     ap.add_argument("--no-train-step", action="store_true")
     ap.add_argument("--no-inloop", action="store_true", help="skip the leg that runs the unmodified reference training loop")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches only (no CUDA-graph replay)")
