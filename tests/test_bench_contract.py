@@ -39,6 +39,25 @@ def test_algorithmic_work_figures():
     assert abs(total / 1e9 - 10.93) < 0.01
 
 
+def test_decode_gemm_flops_and_workload_config():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    D, Dv, F, B, Nv, S = 2304, 1024, 9216, 32, 257, 64
+    rows_all, rows_new = B * S * (S + 1) // 2, B * S
+    per_row_rest = 2 * D * D * 4 + 4 * D * F                  # self q, k, v, o + the two FFN matrices
+    per_row_cross = 2 * D * D * 2                             # w_q, w_o
+    kv = 2 * 2 * (B * Nv) * Dv * D * 2                        # K and V of both blocks, once per image
+    want = kv + per_row_cross * (rows_new + rows_all) + per_row_rest * 2 * rows_all
+    assert bench.decode_gemm_flops(B, S, Nv) == want
+    assert bench.decode_gemm_flops(B, S, Nv, position_rows=False) == want + per_row_cross * (rows_all - rows_new)
+    assert abs(want / 1e12 - 18.57) < 0.01
+    c1, c8 = bench.workload_config(1), bench.workload_config(8)
+    assert "gradients" not in c1 and c1["parallelism"] == "single" and c1["global_batch"] == 8
+    assert "bf16 arena" in c8["gradients"] and c8["parallelism"] == "dp8" and c8["global_batch"] == 64
+    assert "model" not in c1 and c1["workload"].startswith("C2")
+
+
 def test_torch_library_arm_is_the_same_arithmetic():
     """bench.py's `torch_library` comparison (PyTorch's stock operators) computes the bridge: equal to the
     oracle in fp32 on the CPU at small dims, forward and gradients."""

@@ -54,3 +54,35 @@ def test_kernel_choice_per_prefix_length():
     assert m._kv_flag(c, 8, False) == ("kv", 0)            # active dropout: the training kernel draws the masks
     m2 = BridgeLite(vision_dim=32, language_dim=96, num_heads_cross=2, num_heads_self=1).eval()                # d = 48
     assert m2._kv_flag(_cache(), 8, False) == ("kv", 0)    # head dims the decode kernels are not built for
+
+
+def test_cache_constructor_and_refill_argument_rules():
+    """Checks that fail before any kernel is touched (so they can run without a GPU)."""
+    from vlm_bridge_b200 import VisionKVCache
+
+    bridge = types.SimpleNamespace()
+    with pytest.raises(RuntimeError, match=r"\[B, Nv, vision_dim\]"):
+        VisionKVCache(bridge, torch.randn(5, 32))
+    with pytest.raises(ValueError, match="precision"):
+        VisionKVCache(bridge, torch.randn(1, 5, 32), precision="fp16")
+    c = _cache(batch=2)
+    c._bridge, c.precision = bridge, "bf16"
+    with pytest.raises(RuntimeError, match="refill needs"):
+        c.refill(torch.randn(3, 5, 32))                    # another batch size than the cache was built for
+    with pytest.raises(RuntimeError, match="refill needs"):
+        c.refill(torch.randn(2, 6, 32))                    # another number of vision tokens
+
+
+def test_greedy_decode_argument_rules():
+    from vlm_bridge_b200 import greedy_decode
+
+    bridge = types.SimpleNamespace(training=False, eval=lambda: None, train=lambda mode=True: None)
+    v = torch.randn(1, 5, 32)
+    with pytest.raises(ValueError, match="precision"):
+        greedy_decode(bridge, v, None, None, bos_token_id=2, precision="tf32")
+    with pytest.raises(RuntimeError, match="use_cache must stay True"):
+        greedy_decode(bridge, v, None, None, bos_token_id=2, precision="fp32", use_cache=False)
+    c = _cache(batch=1)
+    c.precision = "bf16"
+    with pytest.raises(RuntimeError, match="holds bf16 K/V"):
+        greedy_decode(bridge, v, None, None, bos_token_id=2, precision="fp32", kv_cache=c)

@@ -54,8 +54,9 @@ class MultiHeadCrossAttention(nn.Module):
         B, Lq, _ = query.shape
         Lk = key.shape[1]
         q = _project(_rows_bf16(query), self.w_q)
-        k = _project(_rows_bf16(key), self.w_k)
-        v = k if (value is key and self.w_v is self.w_k) else _project(_rows_bf16(value), self.w_v)
+        k16 = _rows_bf16(key)
+        k = _project(k16, self.w_k)
+        v = _project(k16 if value is key else _rows_bf16(value), self.w_v)
         o = _attend(q, k, v, B, Lq, Lk, self.num_heads, self.d_k)
         return _project(o, self.w_o).float().view(B, Lq, self.query_dim)
 
