@@ -94,8 +94,11 @@ def _bwd(q, k, v, o, lse, d_o, kw):
 
 
 # backward shapes: the tcgen05 path covers query blocks of up to 128 rows; (1, 8, 288, 200, 300) must fall back cleanly
+# (6, 8, 288, 128, 1370): 11 key blocks x 48 (image, head) pairs exceed two waves of CTAs, so the key-major pass walks
+# several key blocks per CTA (the C5 stress shape does the same at batch 16)
 BWD_SHAPES = [(2, 8, 288, 128, 257), (2, 18, 128, 128, 128), (1, 8, 288, 128, 1370), (3, 8, 288, 65, 40),
-              (2, 2, 64, 70, 100), (1, 1, 128, 100, 17), (2, 8, 288, 24, 33), (1, 8, 288, 200, 300)]
+              (2, 2, 64, 70, 100), (1, 1, 128, 100, 17), (2, 8, 288, 24, 33), (1, 8, 288, 200, 300),
+              (6, 8, 288, 128, 1370)]
 
 
 @pytest.mark.parametrize("B,H,HD,Lq,Lk", BWD_SHAPES)
@@ -124,7 +127,7 @@ def test_backward_matches_fp32_autograd_and_legacy_kernels(B, H, HD, Lq, Lk):
         assert float((b_ - r).abs().max()) <= 1.5e-2 * scale, name + " (legacy)"
 
 
-@pytest.mark.parametrize("B,H,HD,Lq,Lk", BWD_SHAPES[:5])
+@pytest.mark.parametrize("B,H,HD,Lq,Lk", BWD_SHAPES[:5] + BWD_SHAPES[-1:])
 def test_backward_with_dropout_regenerates_the_forward_mask(B, H, HD, Lq, Lk):
     """Same seed -> the tcgen05 and the mma.sync kernels draw the same mask in forward and backward, so all four
     combinations agree; a wrong mask in either backward pass would show as an O(1) relative error."""

@@ -574,30 +574,41 @@ template <int HD>
 __global__ void __launch_bounds__(kFThreads, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                        const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
-                       const BwdTcParams p) {
+                       const BwdTcParams p, const int blocks_per_cta) {
   using Cfg = DkvTcCfg<HD>;
   extern __shared__ uint8_t smem_ftc_raw[];
-  __shared__ __align__(8) uint64_t kq_full, do_full, v_full, a_free, st_full, dpt_full, pds_full, dv_done, dv_drained, dk_done;
+  // q_full / do_full: the query block's Q / dO landed (once per CTA). Per key block `it` of this CTA (phase it & 1):
+  // k_full / v_full: K_j / V_j landed in the A buffer; k_free / v_free: S^T / dP^T have consumed it;
+  // st_full / dpt_full: S^T / dP^T produced; pds_full: P^T and dS^T stored; dv_done / dk_done: dV / dK produced;
+  // dv_drained / dk_drained: the output columns have been read out
+  __shared__ __align__(8) uint64_t q_full, do_full, k_full, v_full, k_free, v_free, st_full, dpt_full, pds_full, dv_done,
+      dv_drained, dk_done, dk_drained;
   __shared__ uint32_t tmem_base_smem;
   __shared__ float lse_s[kFBM], del_s[kFBM];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j0 = blockIdx.x * kFBM, h = blockIdx.y, b = blockIdx.z;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int nkb = (p.Lk + kFBM - 1) / kFBM;
+  const int jb0 = blockIdx.x * blocks_per_cta;
+  const int nit = min(blocks_per_cta, nkb - jb0);         // key blocks of this CTA (>= 1 by construction of the grid)
   const uint32_t s0 = (smem_u32(smem_ftc_raw) + 1023u) & ~1023u;
   const uint32_t a_tile = s0, q_tile = s0 + Cfg::kTileBytes, do_tile = q_tile + Cfg::kTileBytes;
   const size_t bh = (size_t)b * p.H + h;
 
   if (threadIdx.x == 0) {
-    mbar_init(&kq_full, 1);
+    mbar_init(&q_full, 1);
     mbar_init(&do_full, 1);
+    mbar_init(&k_full, 1);
     mbar_init(&v_full, 1);
-    mbar_init(&a_free, 1);
+    mbar_init(&k_free, 1);
+    mbar_init(&v_free, 1);
     mbar_init(&st_full, 1);
     mbar_init(&dpt_full, 1);
     mbar_init(&pds_full, 4);
     mbar_init(&dv_done, 1);
     mbar_init(&dv_drained, 4);
     mbar_init(&dk_done, 1);
+    mbar_init(&dk_drained, 4);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -624,164 +635,189 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 
   if (warp == 5) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(&kq_full, 2 * Cfg::kTileBytes);
+      mbar_arrive_expect_tx(&q_full, Cfg::kTileBytes);
 #pragma unroll
-      for (int c = 0; c < Cfg::kChunks; ++c) {
-        tma_load_4d(a_tile + (uint32_t)c * kFBM * 64, &tm_k, smem_u32(&kq_full), c * 32, h, j0, b);
-        tma_load_4d(q_tile + (uint32_t)c * kFBM * 64, &tm_q, smem_u32(&kq_full), c * 32, h, 0, b);
+      for (int c = 0; c < Cfg::kChunks; ++c)
+        tma_load_4d(q_tile + (uint32_t)c * kFBM * 64, &tm_q, smem_u32(&q_full), c * 32, h, 0, b);
+      for (int it = 0; it < nit; ++it) {
+        const int j0 = (jb0 + it) * kFBM;
+        const uint32_t prev = (uint32_t)((it - 1) & 1);
+        if (it >= 1) mbar_wait(&v_free, prev);       // dP^T of the previous key block has consumed V in the A buffer
+        mbar_arrive_expect_tx(&k_full, Cfg::kTileBytes);
+#pragma unroll
+        for (int c = 0; c < Cfg::kChunks; ++c)
+          tma_load_4d(a_tile + (uint32_t)c * kFBM * 64, &tm_k, smem_u32(&k_full), c * 32, h, j0, b);
+        if (it == 0) {
+          mbar_arrive_expect_tx(&do_full, Cfg::kTileBytes);
+#pragma unroll
+          for (int c = 0; c < Cfg::kChunks; ++c)
+            tma_load_4d(do_tile + (uint32_t)c * kFBM * 64, &tm_do, smem_u32(&do_full), c * 32, h, 0, b);
+        }
+        mbar_wait(&k_free, (uint32_t)(it & 1));      // S^T has consumed K_j: V_j takes its place
+        mbar_arrive_expect_tx(&v_full, Cfg::kTileBytes);
+#pragma unroll
+        for (int c = 0; c < Cfg::kChunks; ++c)
+          tma_load_4d(a_tile + (uint32_t)c * kFBM * 64, &tm_v, smem_u32(&v_full), c * 32, h, j0, b);
       }
-      mbar_arrive_expect_tx(&do_full, Cfg::kTileBytes);
-#pragma unroll
-      for (int c = 0; c < Cfg::kChunks; ++c)
-        tma_load_4d(do_tile + (uint32_t)c * kFBM * 64, &tm_do, smem_u32(&do_full), c * 32, h, 0, b);
-      mbar_wait(&a_free, 0);      // S^T has consumed K_j: V_j takes its place
-      mbar_arrive_expect_tx(&v_full, Cfg::kTileBytes);
-#pragma unroll
-      for (int c = 0; c < Cfg::kChunks; ++c)
-        tma_load_4d(a_tile + (uint32_t)c * kFBM * 64, &tm_v, smem_u32(&v_full), c * 32, h, j0, b);
     }
   } else if (warp == 4) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(kFBM, kFBM, false, false);
       constexpr uint32_t idesc_o0 = umma_idesc_bf16(kFBM, Cfg::kN0, false, true);
       constexpr uint32_t idesc_o1 = umma_idesc_bf16(kFBM, Cfg::kN1 > 0 ? Cfg::kN1 : 16, false, true);
-      mbar_wait(&kq_full, 0);
-      tc_fence_after();
-#pragma unroll
-      for (int ks = 0; ks < HD / 16; ++ks)
-        umma_bf16(tmem_base + Cfg::kStCol, desc_sw64_kmajor(a_tile, kFBM, ks), desc_sw64_kmajor(q_tile, kFBM, ks), idesc_s,
-                  ks > 0);
-      umma_commit(&st_full);
-      umma_commit(&a_free);
-      mbar_wait(&do_full, 0);
-      mbar_wait(&v_full, 0);
-      tc_fence_after();
-#pragma unroll
-      for (int ks = 0; ks < HD / 16; ++ks)
-        umma_bf16(tmem_base + Cfg::kDptCol, desc_sw64_kmajor(a_tile, kFBM, ks), desc_sw64_kmajor(do_tile, kFBM, ks),
-                  idesc_s, ks > 0);
-      umma_commit(&dpt_full);
-      mbar_wait(&pds_full, 0);
-      tc_fence_after();
       const uint32_t od = tmem_base + (uint32_t)Cfg::kOutCol;
+      mbar_wait(&q_full, 0);
+      for (int it = 0; it < nit; ++it) {
+        const uint32_t ph = (uint32_t)(it & 1);
+        // S^T overwrites the columns P^T(it - 1) lived in: dV(it - 1) has read them (dv_done was waited for by the
+        // epilogue before dv_drained, which this thread waited for before issuing dK(it - 1))
+        mbar_wait(&k_full, ph);
+        tc_fence_after();
 #pragma unroll
-      for (int kc = 0; kc < kFBM / 16; ++kc) {      // dV = Pd^T dO
-        umma_bf16_tmem_a(od, tmem_base + (uint32_t)(Cfg::kStCol + kc * 8), desc_sw64_mnmajor(do_tile, kFBM, 0, kc),
-                         idesc_o0, kc != 0);
-        if constexpr (Cfg::kN1 > 0)
-          umma_bf16_tmem_a(od + (uint32_t)Cfg::kN0, tmem_base + (uint32_t)(Cfg::kStCol + kc * 8),
-                           desc_sw64_mnmajor(do_tile, kFBM, Cfg::kN0 / 32, kc), idesc_o1, kc != 0);
-      }
-      umma_commit(&dv_done);
-      mbar_wait(&dv_drained, 0);
-      tc_fence_after();
+        for (int ks = 0; ks < HD / 16; ++ks)
+          umma_bf16(tmem_base + Cfg::kStCol, desc_sw64_kmajor(a_tile, kFBM, ks), desc_sw64_kmajor(q_tile, kFBM, ks), idesc_s,
+                    ks > 0);
+        umma_commit(&st_full);
+        umma_commit(&k_free);
+        if (it == 0) mbar_wait(&do_full, 0);
+        mbar_wait(&v_full, ph);
+        tc_fence_after();
+        // dP^T overwrites the columns dS^T(it - 1) lived in; dK(it - 1), issued earlier by this thread, completes first
 #pragma unroll
-      for (int kc = 0; kc < kFBM / 16; ++kc) {      // dK = dS^T Q
-        umma_bf16_tmem_a(od, tmem_base + (uint32_t)(Cfg::kDptCol + kc * 8), desc_sw64_mnmajor(q_tile, kFBM, 0, kc),
-                         idesc_o0, kc != 0);
-        if constexpr (Cfg::kN1 > 0)
-          umma_bf16_tmem_a(od + (uint32_t)Cfg::kN0, tmem_base + (uint32_t)(Cfg::kDptCol + kc * 8),
-                           desc_sw64_mnmajor(q_tile, kFBM, Cfg::kN0 / 32, kc), idesc_o1, kc != 0);
+        for (int ks = 0; ks < HD / 16; ++ks)
+          umma_bf16(tmem_base + Cfg::kDptCol, desc_sw64_kmajor(a_tile, kFBM, ks), desc_sw64_kmajor(do_tile, kFBM, ks),
+                    idesc_s, ks > 0);
+        umma_commit(&dpt_full);
+        umma_commit(&v_free);
+        mbar_wait(&pds_full, ph);
+        if (it >= 1) mbar_wait(&dk_drained, (uint32_t)((it - 1) & 1));   // the output columns still hold dK(it - 1)
+        tc_fence_after();
+#pragma unroll
+        for (int kc = 0; kc < kFBM / 16; ++kc) {      // dV = Pd^T dO
+          umma_bf16_tmem_a(od, tmem_base + (uint32_t)(Cfg::kStCol + kc * 8), desc_sw64_mnmajor(do_tile, kFBM, 0, kc),
+                           idesc_o0, kc != 0);
+          if constexpr (Cfg::kN1 > 0)
+            umma_bf16_tmem_a(od + (uint32_t)Cfg::kN0, tmem_base + (uint32_t)(Cfg::kStCol + kc * 8),
+                             desc_sw64_mnmajor(do_tile, kFBM, Cfg::kN0 / 32, kc), idesc_o1, kc != 0);
+        }
+        umma_commit(&dv_done);
+        mbar_wait(&dv_drained, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kc = 0; kc < kFBM / 16; ++kc) {      // dK = dS^T Q
+          umma_bf16_tmem_a(od, tmem_base + (uint32_t)(Cfg::kDptCol + kc * 8), desc_sw64_mnmajor(q_tile, kFBM, 0, kc),
+                           idesc_o0, kc != 0);
+          if constexpr (Cfg::kN1 > 0)
+            umma_bf16_tmem_a(od + (uint32_t)Cfg::kN0, tmem_base + (uint32_t)(Cfg::kDptCol + kc * 8),
+                             desc_sw64_mnmajor(q_tile, kFBM, Cfg::kN0 / 32, kc), idesc_o1, kc != 0);
+        }
+        umma_commit(&dk_done);
       }
-      umma_commit(&dk_done);
     }
   } else {
     const DropoutCfg drop = dropout_resolve(p.drop);
     const int row = warp * 32 + lane;          // key j0 + row lives on TMEM lane `row`
-    const int key = j0 + row;
-    const bool key_ok = key < p.Lk;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    const uint64_t kgrp = (uint64_t)((j0 + warp * 32) >> 3) + (uint64_t)(lane >> 3);   // this lane's Philox key group
-    mbar_wait(&st_full, 0);
-    mbar_wait(&dpt_full, 0);
-    tc_fence_after();
+    for (int it = 0; it < nit; ++it) {
+      const uint32_t ph = (uint32_t)(it & 1);
+      const int j0 = (jb0 + it) * kFBM;
+      const int key = j0 + row;
+      const bool key_ok = key < p.Lk;
+      const uint64_t kgrp = (uint64_t)((j0 + warp * 32) >> 3) + (uint64_t)(lane >> 3);   // this lane's Philox key group
+      mbar_wait(&st_full, ph);
+      mbar_wait(&dpt_full, ph);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < kFBM / 32; ++c) {      // 32 queries per slice
-      uint32_t sv[2][16], dv[2][16];
+      for (int c = 0; c < kFBM / 32; ++c) {      // 32 queries per slice
+        uint32_t sv[2][16], dv[2][16];
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kStCol + c * 32 + g * 16), sv[g]);
-        tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kDptCol + c * 32 + g * 16), dv[g]);
-      }
-      tmem_ld_wait();
-      // dropout bits of the slice: lane L evaluates (query c*32 + r*8 + (L & 7), key group L >> 3) for r = 0..3
-      uint4 bits[4];
-      if (drop.thr != 0) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const uint64_t qi = (uint64_t)(c * 32 + r * 8 + (lane & 7));
-          bits[r] = dropout_bits8(drop, p.drop_stream, ((bh * p.Lq + qi) * (uint64_t)p.Lkp >> 3) + kgrp);
+        for (int g = 0; g < 2; ++g) {
+          tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kStCol + c * 32 + g * 16), sv[g]);
+          tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kDptCol + c * 32 + g * 16), dv[g]);
         }
-      }
-      uint32_t wp[16], wd[16];
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        float pv[16], dsv[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int qi = c * 32 + g * 16 + j;       // query index inside the block
-          float pr = (key_ok && qi < p.Lq) ? exp2f(__uint_as_float(sv[g][j]) * p.scale_log2 - lse_s[qi]) : 0.f;
-          float dpr = __uint_as_float(dv[g][j]);
-          float prd = pr;
-          if (drop.thr != 0) {
-            const int r = (g * 16 + j) >> 3, m = (g * 16 + j) & 7;
-            const int src = (lane & 24) | m;
-            uint4 bb;
-            bb.x = __shfl_sync(0xffffffffu, bits[r].x, src);
-            bb.y = __shfl_sync(0xffffffffu, bits[r].y, src);
-            bb.z = __shfl_sync(0xffffffffu, bits[r].z, src);
-            bb.w = __shfl_sync(0xffffffffu, bits[r].w, src);
-            const bool keep = dropout_keep(bb, lane & 7, drop.thr);
-            prd = keep ? pr * drop.scale : 0.f;
-            dpr = keep ? dpr * drop.scale : 0.f;
-          }
-          pv[j] = prd;
-          dsv[j] = pr * (dpr - del_s[qi]);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          wp[g * 8 + j] = pack_bf16(pv[2 * j], pv[2 * j + 1]);
-          wd[g * 8 + j] = pack_bf16(dsv[2 * j], dsv[2 * j + 1]);
-        }
-      }
-      // in place: the bf16 slice [16c, 16c + 16) lies inside the fp32 columns [0, 32c + 32) already consumed
-      tmem_st_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kStCol + c * 16), wp);
-      tmem_st_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kDptCol + c * 16), wd);
-    }
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&pds_full);
-    auto drain = [&](__nv_bfloat16* base, long long ld, float mul) {
-      __nv_bfloat16* dst = base + ((size_t)b * p.Lk + (key_ok ? key : 0)) * ld + (size_t)h * HD;
-#pragma unroll 1
-      for (int c0 = 0; c0 < HD; c0 += 32) {
-        uint32_t v0[16], v1[16];
-        tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kOutCol + c0), v0);
-        tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kOutCol + c0 + 16), v1);
         tmem_ld_wait();
-        if (key_ok) {
-          uint4 u[4];
-          uint32_t* w = reinterpret_cast<uint32_t*>(u);
+        // dropout bits of the slice: lane L evaluates (query c*32 + r*8 + (L & 7), key group L >> 3) for r = 0..3
+        uint4 bits[4];
+        if (drop.thr != 0) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const uint64_t qi = (uint64_t)(c * 32 + r * 8 + (lane & 7));
+            bits[r] = dropout_bits8(drop, p.drop_stream, ((bh * p.Lq + qi) * (uint64_t)p.Lkp >> 3) + kgrp);
+          }
+        }
+        uint32_t wp[16], wd[16];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float pv[16], dsv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int qi = c * 32 + g * 16 + j;       // query index inside the block
+            float pr = (key_ok && qi < p.Lq) ? exp2f(__uint_as_float(sv[g][j]) * p.scale_log2 - lse_s[qi]) : 0.f;
+            float dpr = __uint_as_float(dv[g][j]);
+            float prd = pr;
+            if (drop.thr != 0) {
+              const int r = (g * 16 + j) >> 3, m = (g * 16 + j) & 7;
+              const int src = (lane & 24) | m;
+              uint4 bb;
+              bb.x = __shfl_sync(0xffffffffu, bits[r].x, src);
+              bb.y = __shfl_sync(0xffffffffu, bits[r].y, src);
+              bb.z = __shfl_sync(0xffffffffu, bits[r].z, src);
+              bb.w = __shfl_sync(0xffffffffu, bits[r].w, src);
+              const bool keep = dropout_keep(bb, lane & 7, drop.thr);
+              prd = keep ? pr * drop.scale : 0.f;
+              dpr = keep ? dpr * drop.scale : 0.f;
+            }
+            pv[j] = prd;
+            dsv[j] = pr * (dpr - del_s[qi]);
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            w[j] = pack_bf16(__uint_as_float(v0[2 * j]) * mul, __uint_as_float(v0[2 * j + 1]) * mul);
-            w[8 + j] = pack_bf16(__uint_as_float(v1[2 * j]) * mul, __uint_as_float(v1[2 * j + 1]) * mul);
+            wp[g * 8 + j] = pack_bf16(pv[2 * j], pv[2 * j + 1]);
+            wd[g * 8 + j] = pack_bf16(dsv[2 * j], dsv[2 * j + 1]);
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + c0 + j * 8) = u[j];
         }
+        // in place: the bf16 slice [16c, 16c + 16) lies inside the fp32 columns [0, 32c + 32) already consumed
+        tmem_st_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kStCol + c * 16), wp);
+        tmem_st_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kDptCol + c * 16), wd);
       }
-    };
-    mbar_wait(&dv_done, 0);
-    tc_fence_after();
-    drain(p.dv, p.lddv, 1.0f);
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&dv_drained);
-    mbar_wait(&dk_done, 0);
-    tc_fence_after();
-    drain(p.dk, p.lddk, p.scale);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pds_full);
+      auto drain = [&](__nv_bfloat16* base, long long ld, float mul) {
+        __nv_bfloat16* dst = base + ((size_t)b * p.Lk + (key_ok ? key : 0)) * ld + (size_t)h * HD;
+#pragma unroll 1
+        for (int c0 = 0; c0 < HD; c0 += 32) {
+          uint32_t v0[16], v1[16];
+          tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kOutCol + c0), v0);
+          tmem_ld_32x32_x16(tmem_base + lane_off + (uint32_t)(Cfg::kOutCol + c0 + 16), v1);
+          tmem_ld_wait();
+          if (key_ok) {
+            uint4 u[4];
+            uint32_t* w = reinterpret_cast<uint32_t*>(u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              w[j] = pack_bf16(__uint_as_float(v0[2 * j]) * mul, __uint_as_float(v0[2 * j + 1]) * mul);
+              w[8 + j] = pack_bf16(__uint_as_float(v1[2 * j]) * mul, __uint_as_float(v1[2 * j + 1]) * mul);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + c0 + j * 8) = u[j];
+          }
+        }
+      };
+      mbar_wait(&dv_done, ph);
+      tc_fence_after();
+      drain(p.dv, p.lddv, 1.0f);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dv_drained);
+      mbar_wait(&dk_done, ph);
+      tc_fence_after();
+      drain(p.dk, p.lddk, p.scale);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dk_drained);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -827,8 +863,20 @@ static int launch_bwd_tc(const b200b_attn_args* a, const float* delta, cudaStrea
   // key-major pass: K / V blocks of 128 keys
   if ((rc = make_tmap_heads_sw64(&tk, a->k, a->ldk, HD, a->heads, a->len_k, a->batch, kFBM)) != B200B_OK) return rc;
   if ((rc = make_tmap_heads_sw64(&tv, a->v, a->ldv, HD, a->heads, a->len_k, a->batch, kFBM)) != B200B_OK) return rc;
-  dim3 gk((a->len_k + kFBM - 1) / kFBM, a->heads, a->batch);
-  launch_pdl(kPdlAttn, attn_bwd_dkv_tc_kernel<HD>, gk, dim3(kFThreads), DkvTcCfg<HD>::kSmemBytes, stream, tq, td, tk, tv, p);
+  // Key blocks per CTA: one while the grid fits two waves of the SMs (a CTA re-loads the query block's Q and dO, 2 tiles
+  // of the 3 it holds, for every key block), more for long key sequences (1370 vision tokens = 11 key blocks per head)
+  // so that Q / dO are fetched once per CTA and the blocks of a head are spread evenly over its CTAs.
+  int num_sms = 0;
+  if ((rc = device_sm_count(&num_sms)) != B200B_OK) return rc;
+  const int nkb = (a->len_k + kFBM - 1) / kFBM;
+  const long long items = (long long)nkb * a->heads * a->batch;
+  int bpc = (int)((items + 2LL * num_sms - 1) / (2LL * num_sms));
+  if (bpc < 1) bpc = 1;
+  const int ctas_per_head = (nkb + bpc - 1) / bpc;
+  bpc = (nkb + ctas_per_head - 1) / ctas_per_head;
+  dim3 gk((nkb + bpc - 1) / bpc, a->heads, a->batch);
+  launch_pdl(kPdlAttn, attn_bwd_dkv_tc_kernel<HD>, gk, dim3(kFThreads), DkvTcCfg<HD>::kSmemBytes, stream, tq, td, tk, tv, p,
+             bpc);
   return check_launch("attn_bwd_dkv_tc", stream);
 }
 
