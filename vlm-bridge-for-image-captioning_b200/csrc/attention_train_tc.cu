@@ -546,8 +546,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 // =====================================================================================================
 // backward, key-major: dV = Pd^T dO, dK = scale * dS^T Q, for query blocks of up to 128 rows (the training shapes)
 // =====================================================================================================
-// One CTA per (128 keys, head, image), TRANSPOSED formulation: S^T = K_j Q^T and dP^T = V_j dO^T put a key on every
-// TMEM lane, so P^T and dS^T come out in exactly the layout the tensor-memory A operand of dV = P^T dO and
+// One CTA per (key block(s) of 128 keys, head, image) -- one block while the grid fits two waves of the SMs, several
+// consecutive blocks with Q / dO kept resident for long key sequences -- in a TRANSPOSED formulation:
+// S^T = K_j Q^T and dP^T = V_j dO^T put a key on every TMEM lane, so P^T and dS^T come out in exactly the layout the tensor-memory A operand of dV = P^T dO and
 // dK = dS^T Q needs (lane = key = output row, columns = queries = contraction index); dO and Q are then read a second
 // time from the SAME shared-memory tiles as MN-major B operands. Three 128 x HD tiles are resident (K_j, later
 // overwritten by V_j; Q; dO) -- 221 KB at HD = 288. The bf16 P^T / dS^T overwrite the fp32 S^T / dP^T columns they
